@@ -1,0 +1,44 @@
+"""Seeded inputs shared by tests/golden/make_golden.py (which runs the reference) and the parity tests."""
+import zlib
+
+import torch
+
+from osmosis_diffusion_code_b200.synthetic import synth_measurement
+
+# create_model(**SMALL_UNET): same block types / channels-per-group as the shipped config, small spatially.
+SMALL_UNET = dict(image_size=32, num_channels=256, num_res_blocks=1, channel_mult="1,2", learn_sigma=True,
+                  class_cond=False, use_checkpoint=False, attention_resolutions="16", num_heads=4,
+                  num_head_channels=64, num_heads_upsample=-1, use_scale_shift_norm=True, dropout=0.0,
+                  resblock_updown=True, use_fp16=False, use_new_attention_order=False, pretrain_model="osmosis")
+SMALL_HW = 32
+
+CASES = {
+    "osmosis": dict(yaml="osmosis_sample_config.yaml", respacing=6, post_idx=[5, 2], step_idx=[5, 3, 0]),
+    "simulation": dict(yaml="osmosis_simulation_sample_config.yaml", respacing=6, post_idx=[4], step_idx=[5, 2]),
+    "haze": dict(yaml="osmosis_haze_sample_config.yaml", respacing=6, post_idx=[1], step_idx=[5, 1]),
+}
+
+_MEAS = {
+    "osmosis": dict(phi_a=(1.1, 0.95, 0.95), phi_b=(0.95, 0.8, 0.8), phi_inf=(0.14, 0.29, 0.49), depth_type="gamma"),
+    "simulation": dict(phi_a=(1.1, 0.95, 0.95), phi_b=(1.1, 0.95, 0.95), phi_inf=(0.2, 0.4, 0.7), depth_type="original"),
+    "haze": dict(phi_a=(1.0,), phi_b=(1.0,), phi_inf=(0.14, 0.29, 0.49), depth_type="gamma"),
+}
+
+
+def _gen(key: str) -> torch.Generator:
+    return torch.Generator().manual_seed(zlib.crc32(key.encode()))
+
+
+def case_inputs(key: str):
+    if key == "unet":
+        g = _gen(key)
+        x = torch.randn(2, 4, SMALL_HW, SMALL_HW, generator=g)
+        t = torch.tensor([37, 512])
+        cot = torch.randn(2, 8, SMALL_HW, SMALL_HW, generator=g)
+        return x, t, cot
+    kind, *rest = key.split(":")
+    if kind == "meas":
+        return synth_measurement(3, SMALL_HW, **_MEAS[rest[0]])
+    if kind in ("x", "noise"):
+        return torch.randn(1, 4, SMALL_HW, SMALL_HW, generator=_gen(key))
+    raise KeyError(key)
