@@ -1,0 +1,164 @@
+/* osmosis_b200.h - C ABI of the B200-native Osmosis guided-sampling path.
+ *
+ * The reference (osmosis-diffusion/osmosis-diffusion-code) is pure Python/PyTorch and has no FFI; its
+ * "plugin API" is the Python registry/factory surface (create_model / create_sampler / get_operator /
+ * get_conditioning_method).  Each entry point below is what that surface binds underneath in this
+ * repo; the comment on each names the reference call it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative code on failure; osm_last_error_string()
+ *     returns the message of the last failure on the calling thread.  Nothing throws.
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name says `host`.
+ *   - tensors crossing the boundary are NCHW fp32, contiguous (the reference's layout).
+ *   - every launch goes to the given cudaStream_t (passed as void*); no hidden host sync, no
+ *     allocation after osm_unet_create / osm_unet_load_param / osm_unet_bind.
+ *   - B > 1 means B independent B=1 reference runs (per-image loss norm / aux means).
+ */
+#ifndef OSMOSIS_B200_H_
+#define OSMOSIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSM_OK 0
+#define OSM_ERR_INVALID (-1)
+#define OSM_ERR_CUDA (-2)
+#define OSM_ERR_STATE (-3)
+
+const char* osm_last_error_string(void);
+/* ABI version of this header; bumped on any signature change. */
+int osm_abi_version(void);
+
+/* ------------------------------------------------------------------ UNet ------------------------------
+ * replaces guided_diffusion/unet.py: create_model :27-98, UNetModel.__init__ :503-695,
+ * UNetModel.forward :713-742 and (for the input gradient) the autograd graph that
+ * condition_methods.py:186-191 back-propagates through.                                              */
+typedef struct osm_unet_config {
+  int in_channels;        /* 4  (RGBD)                                   utils.py:265-288            */
+  int out_channels;       /* 8  (eps | learned-range variance)                                       */
+  int model_channels;     /* num_channels                                unet.py:29                  */
+  int num_res_blocks;     /*                                             unet.py:30                  */
+  int num_levels;         /* len(channel_mult)                                                       */
+  int channel_mult[8];    /*                                             unet.py:47-59               */
+  int num_attention_ds;   /* number of entries in attention_ds                                       */
+  int attention_ds[8];    /* downsample rates with attention             unet.py:61-66               */
+  int num_heads;          /* used when num_head_channels == -1                                       */
+  int num_head_channels;  /* 64 in every shipped config                                              */
+  int conv_mode;          /* 0: tcgen05 TF32 tensor-core convs (product path), 1: fp32 CUDA-core convs
+                             (exact mode used to separate precision from logic in parity tests)       */
+} osm_unet_config;
+
+typedef struct osm_unet* osm_unet_t;
+
+int osm_unet_create(const osm_unet_config* cfg, osm_unet_t* out);
+int osm_unet_destroy(osm_unet_t h);
+/* Parameter table in guided-diffusion state_dict order/names (OIHW fp32).  Host-only, no GPU needed. */
+int osm_unet_param_count(osm_unet_t h);
+int osm_unet_param_info(osm_unet_t h, int index, const char** name, int* ndim, int64_t shape[4]);
+/* Copies + repacks one state_dict tensor (host fp32, contiguous) into the engine's device layout.
+ * replaces model.load_state_dict (unet.py:94-97).                                                    */
+int osm_unet_load_param(osm_unet_t h, const char* name, const float* host_data, int64_t numel, void* stream);
+/* Bytes of caller-provided device workspace needed for batch B at HxW (activations kept for the input
+ * VJP, gradients, scratch).                                                                          */
+int64_t osm_unet_workspace_bytes(osm_unet_t h, int B, int H, int W);
+/* Builds the launch plan (buffer offsets, TMA descriptors) for (B,H,W) on `workspace`.               */
+int osm_unet_bind(osm_unet_t h, int B, int H, int W, void* workspace, int64_t workspace_bytes);
+/* out[B,out_ch,H,W] = UNet(x[B,in_ch,H,W], t[B]); t are the (possibly fractional) model timesteps as
+ * fp32 (the reference's timesteps.float(), nn.py:116).  Keeps what the VJP needs in the workspace.   */
+int osm_unet_forward(osm_unet_t h, const float* x, const float* t, float* out, void* stream);
+/* grad_x[B,in_ch,H,W] = d<out, grad_out>/dx for the most recent forward (input gradient only - the
+ * reference requests no weight gradients: condition_methods.py:188-191).                             */
+int osm_unet_vjp_input(osm_unet_t h, const float* grad_out, float* grad_x, void* stream);
+/* Number of kernel launches one forward / one vjp issues (bench.py's gpu_launches).                  */
+int osm_unet_launch_count(osm_unet_t h, int which /*0 fwd, 1 vjp*/);
+/* Algorithmic FLOPs (2*MAC) of one forward for the bound shape (convs + attention + linear).         */
+double osm_unet_forward_flops(osm_unet_t h);
+
+/* ------------------------------------------------------------- sampler elementwise ---------------------
+ * coef: [T][8] fp32 rows = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+ * posterior_mean_coef2, log(beta), posterior_log_variance_clipped, 0, 0}, each the fp32 rounding of the
+ * reference's float64 table entry (posterior_mean_variance.py:265-269).  t_idx[B]: int32 respaced index. */
+
+/* replaces EpsilonXMeanProcessor.get_mean_and_xstart (posterior_mean_variance.py:104-136) and
+ * LearnedRangeVarianceProcessor.get_variance (:227-258), as called from p_mean_variance
+ * (gaussian_diffusion.py:345-365).  model_out [B,2C,HW]; x, x0, mean, logvar [B,C,HW].                */
+int osm_posterior_fwd(const float* coef, const int32_t* t_idx, const float* x, const float* model_out, float* x0,
+                      float* mean, float* logvar, int B, int C, int HW, void* stream);
+/* VJP of the above: any of g_x0 / g_mean / g_logvar may be NULL (treated as zero).
+ * g_x [B,C,HW] (direct path through x), g_model_out [B,2C,HW].                                        */
+int osm_posterior_vjp(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean,
+                      const float* g_logvar, float* g_x, float* g_model_out, int B, int C, int HW, void* stream);
+/* replaces condition_methods.py:211-223 + gaussian_diffusion.py:266-271:
+ *   x_out = mean - scale[c] * clamp(g_a + g_b, +-clip) + [t_idx != 0] * exp(0.5*logvar) * noise
+ * g_b may be NULL; clip < 0 disables clamping.  The clamped-before-scale raw gradient g_a+g_b is written to
+ * grad_out if non-NULL (the `gradients` the reference returns, condition_methods.py:224).            */
+int osm_sampler_update(const float* mean, const float* g_a, const float* g_b, const float* scale4, float clip,
+                       const float* logvar, const float* noise, const int32_t* t_idx, float* x_out, float* grad_out,
+                       int B, int C, int HW, void* stream);
+/* replaces osmosis_utils/diffusion.py:122 (GaussianDiffusion.inverse, unguided ancestral update):
+ *   x = (x - c_eps * eps) * c_x + c_z * z   with eps = model_out[:, :C]                               */
+int osm_ddpm_uncond_update(float* x, const float* model_out, const float* z, float c_x, float c_eps, float c_z, int B,
+                           int C, int C_model_out, int HW, void* stream);
+
+/* ------------------------------------------------------- measurement operators + guidance --------------*/
+#define OSM_OP_UNDERWATER_REVISED 0 /* measurements.py:211-329  phi_a, phi_b, phi_inf  [B,3] each      */
+#define OSM_OP_UNDERWATER 1         /* measurements.py:332-433  phi_ab, phi_inf                         */
+#define OSM_OP_HAZE 2               /* measurements.py:107-208  scalar phi_ab, phi_inf                  */
+#define OSM_DEPTH_ORIGINAL 0        /* utils.py:560-561  0.5*(d+1)                                      */
+#define OSM_DEPTH_GAMMA 1           /* utils.py:557-558  ((d+v0)*v1)^v2                                 */
+#define OSM_DEPTH_MOVE 2            /* utils.py:554-555  d+v0                                           */
+
+typedef struct osm_guidance_params {
+  int op_kind;           /* OSM_OP_*                                                                    */
+  int depth_kind;        /* OSM_DEPTH_* of the operator                                                 */
+  float depth_val[3];
+  int weight_kind;       /* 0: none, 1: depth (condition_methods.py:121-125, utils.py:674-700)          */
+  int weight_depth_kind; /* OSM_DEPTH_* of weight_function                                              */
+  float weight_val[3];
+  float eta[3];          /* SGD step per phi group in get_variable_list() order (0 if learn flag off)   */
+  int n_iter;            /* inner iterations when not frozen (sample_pattern.n_iter)                    */
+  float gamma_avrg;      /* aux_loss.avrg_loss weight, 0 if absent (losses.py:29-45)                    */
+  float gamma_val;       /* aux_loss.val_loss weight, 0 if absent  (losses.py:51-62)                    */
+} osm_guidance_params;
+
+/* replaces Operator.forward (measurements.py:138-151, 251-264, 363-376): out[B,3,HW] = A_phi(x[B,4,HW]).
+ * phi [B,9] = {a0,a1,a2, b0,b1,b2, inf0,inf1,inf2}; tied operators read a* for both, haze reads a0.   */
+int osm_operator_forward(int op_kind, int depth_kind, const float depth_val[3], const float* x, const float* phi,
+                         float* out, int B, int HW, void* stream);
+/* replaces the whole inner loop of PosteriorSamplingOsmosis.conditioning (condition_methods.py:146-209):
+ * grad_and_value (:109-144) + AuxiliaryLoss.forward (losses.py:67-83) + backward w.r.t. phi and x_0_hat +
+ * operator.optimize (measurements.py:266-303), 1 evaluation if freeze else n_iter, SGD after every
+ * evaluation, x-gradient taken at the last evaluation.  freeze_flag: device int32[1] (non-zero = frozen),
+ * so the same captured launch serves both phases.
+ *   x0 [B,4,HW], y [B,3,HW] -> g_x0 [B,4,HW] (d total_loss / d x_0_hat), phi [B,9] updated in place,
+ *   losses [B,4] = {norm loss (sep_loss), avrg term, val term, total}.                                 */
+int osm_guidance_phi_loop(const osm_guidance_params* p, const float* x0, const float* y, float* phi,
+                          const int32_t* freeze_flag, float* g_x0, float* losses, int B, int HW, void* stream);
+
+/* ------------------------------------------------------------ layer-level entry points -----------------
+ * Used by the kernel parity tests (tests/test_kernels_gpu.py); NHWC fp32 with an explicit pixel stride
+ * `ld` (elements).  Not part of the sampling API.                                                     */
+int osm_dbg_conv(int conv_mode, const float* x, int ldx, const float* w_packed, const float* bias, const float* res,
+                 int ldr, int res_mode, float* out, int ldo, int accumulate, int B, int H, int W, int Cin, int Cout,
+                 int taps, void* stream);
+int osm_dbg_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p,
+                             int taps, int round_tf32, void* stream);
+int osm_dbg_gn_forward(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,
+                       int ld_ss, int silu, int resample, float* stats, float* y, int B, int H, int W, int C, void* stream);
+int osm_dbg_gn_backward(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,
+                        int ld_ss, int silu, int resample, const float* stats, const float* dy, const float* addend,
+                        int ld_add, int add_mode, float* dx, int ld_dx, int accumulate, int B, int H, int W, int C,
+                        void* stream);
+int osm_dbg_attention(const float* qkv, float* out, float* scratch_P, int B, int L, int C, int heads, void* stream);
+int osm_dbg_attention_bwd(const float* qkv, const float* g_out, float* g_qkv, float* scratch_P, float* scratch_D, int B,
+                          int L, int C, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSMOSIS_B200_H_ */

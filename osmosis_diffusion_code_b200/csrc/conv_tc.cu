@@ -1,0 +1,330 @@
+// tcgen05 (5th-gen tensor core) TF32 implicit-GEMM convolution for sm_100a.
+//
+//   out[pixel, co] = sum_{tap, ci} x[pixel + off(tap), ci] * Wp[tap][co][ci]  (+bias, +residual, +=)
+//
+// NHWC fp32 activations, 3x3 (pad 1) or 1x1, stride 1.  Reference call sites: every nn.Conv2d / Conv1d(k=1)
+// of UNetModel (unet.py:264, 290, 301, 365, 373, 561, 694) and, with the flipped/transposed weight pack,
+// their input gradients (condition_methods.py:186-191 back-propagates to x_prev only).
+//
+// Mapping to the hardware
+//   * GEMM view: M = 128 output pixels (a tw x th x tn box of one or more images), N = BN output
+//     channels, K = taps * Cin in blocks of 32 fp32 (one 128-byte swizzle row).
+//   * A tile: ONE 4-D TMA box load {32 ch, tw, th, tn} at coordinates shifted by the tap offset; rows
+//     that fall outside the image are zero-filled by the TMA unit, which IS the conv's zero padding -
+//     no im2col buffer, no halo handling in the kernel.  B tile: 3-D box {32 ci, BN co, 1 tap} of the
+//     packed weights.  Both land in shared memory in the canonical K-major SWIZZLE_128B layout that
+//     tcgen05.mma consumes directly.
+//   * warp 0 / lane 0: TMA producer over a STAGES-deep mbarrier ring; warp 1 / lane 0: issues
+//     tcgen05.mma.kind::tf32 (M128 x N=BN x K8, 4 per stage) accumulating in TMEM, releases stages with
+//     tcgen05.commit; all 4 warps: epilogue (tcgen05.ld 32 lanes x 32 columns -> bias/residual -> 128-bit
+//     stores).
+//   * TF32: the tensor core reads fp32 words from shared memory and ignores the low 13 mantissa bits.
+//     Weights are pre-rounded (RN) at pack time and the GroupNorm/SiLU producer rounds the activation it
+//     writes, so the truncation is exact on both operands wherever the producer is ours.
+#include <cuda.h>
+
+#include "conv_epilogue.cuh"
+
+namespace osm {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (launch error surfaced to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && it > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (1024 B between
+//   8-row groups) | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b_format TF32 (2) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                        // fp32 elements per K block = one 128-byte swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;    // 16 KB
+
+struct ConvTcParams {
+  int taps, kblocks_per_tap;
+  int tw, th, tn, tiles_w, tiles_h;
+  int B, H, W, Cout_p;
+  EpiArgs epi;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tile_w = mt % p.tiles_w; mt /= p.tiles_w;
+  const int tile_h = mt % p.tiles_h; mt /= p.tiles_h;
+  const int w0 = tile_w * p.tw, h0 = tile_h * p.th, n0 = mt * p.tn;
+  const int co0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // one full warp allocates BN TMEM columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int total_k = p.taps * p.kblocks_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int it = 0; it < total_k; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        const int tap = it / p.kblocks_per_tap, kc = it - tap * p.kblocks_per_tap;
+        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+        mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+        tma_load_4d(sa, &tmA, full0 + 8 * s, kc * TC_BK, w0 + dx, h0 + dy, n0);
+        tma_load_3d(sb, &tmB, full0 + 8 * s, kc * TC_BK, co0, tap);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+      for (int it = 0; it < total_k; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {  // UMMA_K = 8 for tf32 = 32 bytes along the swizzled row
+          mma_tf32(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (uint32_t)((it | k) != 0));
+        }
+        tcgen05_commit(empty0 + 8 * s);  // stage reusable once these MMAs have read it
+      }
+      tcgen05_commit(accum_bar);         // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ===== epilogue: all 4 warps; warp w owns TMEM lanes [32w, 32w+32) = tile rows =====
+  mbar_wait(accum_bar, 0);
+  tcgen05_fence_after();
+  const int row = threadIdx.x;
+  const int ww = row % p.tw, hh = (row / p.tw) % p.th, nn = row / (p.tw * p.th);
+  const int w = w0 + ww, h = h0 + hh, n = n0 + nn;
+  const bool row_ok = (w < p.W) && (h < p.H) && (n < p.B);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int co = co0 + c * 32 + j;
+        if (co < p.Cout_p)
+          conv_epilogue_store4(p.epi, n, h, w, co,
+                               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3])));
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int conv_check(const ConvArgs& a);
+
+static void pick_tile(int B, int H, int W, int* tw, int* th, int* tn) {
+  int w = 1;
+  while (w * 2 <= W && w * 2 <= 16) w *= 2;
+  int h = 1;
+  while (h * 2 <= H && w * h * 2 <= TC_BM) h *= 2;
+  *tw = w; *th = h; *tn = TC_BM / (w * h);
+  (void)B;
+}
+
+int conv_tc_plan(const ConvArgs& a, ConvTcPlan* plan) {
+  if (int e = conv_check(a)) return e;
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(OSM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (needs a CUDA 12 driver)");
+  plan->a = a;
+  pick_tile(a.B, a.H, a.W, &plan->tw, &plan->th, &plan->tn);
+  plan->tiles_w = (a.W + plan->tw - 1) / plan->tw;
+  plan->tiles_h = (a.H + plan->th - 1) / plan->th;
+  plan->tiles_b = (a.B + plan->tn - 1) / plan->tn;
+  const long mtiles = (long)plan->tiles_w * plan->tiles_h * plan->tiles_b;
+  // N tile: as wide as possible (operand reuse) while leaving enough CTAs to fill the 148 SMs
+  int BN = 256;
+  while (BN > 32 && (a.Cout_p % BN != 0 || (mtiles * (a.Cout_p / BN) < 148 && BN > 64))) BN /= 2;
+  if (a.Cout_p % BN) BN = 32;
+  plan->BN = BN;
+  plan->stages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  plan->smem_bytes = (size_t)plan->stages * (TC_A_BYTES + BN * TC_BK * 4) + 1024;
+
+  // A: NHWC view as a 4-D tensor {C, W, H, B}
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a.Cin_p, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.ldx * 4, (cuuint64_t)a.W * a.ldx * 4, (cuuint64_t)a.H * a.W * a.ldx * 4};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)plan->tw, (cuuint32_t)plan->th, (cuuint32_t)plan->tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc((CUtensorMap*)plan->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.x, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OSM_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: code " + std::to_string((int)r));
+  }
+  // B: packed weights {Cin_p, Cout_p, taps}
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cin_p, (cuuint64_t)a.Cout_p, (cuuint64_t)a.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)a.Cin_p * 4, (cuuint64_t)a.Cin_p * a.Cout_p * 4};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc((CUtensorMap*)plan->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.w, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OSM_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: code " + std::to_string((int)r));
+  }
+  return OSM_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_t(const ConvTcPlan& pl, const ConvTcParams& p, dim3 grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OSM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)pl.smem_bytes));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN, STAGES><<<grid, 128, pl.smem_bytes, s>>>(*(const CUtensorMap*)pl.tmA, *(const CUtensorMap*)pl.tmB, p);
+  OSM_LAUNCH_CHECK("conv_tc_kernel");
+  return OSM_OK;
+}
+
+int conv_tc_launch(const ConvTcPlan& pl, cudaStream_t s) {
+  const ConvArgs& a = pl.a;
+  ConvTcParams p;
+  p.taps = a.taps; p.kblocks_per_tap = a.Cin_p / TC_BK;
+  p.tw = pl.tw; p.th = pl.th; p.tn = pl.tn; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.B = a.B; p.H = a.H; p.W = a.W; p.Cout_p = a.Cout_p;
+  p.epi = EpiArgs{a.bias, a.res, a.ldr, a.res_mode, a.out, a.ldo, a.accumulate, a.H, a.W};
+  dim3 grid((unsigned)((long)pl.tiles_w * pl.tiles_h * pl.tiles_b), (unsigned)(a.Cout_p / pl.BN));
+  switch (pl.BN) {
+    case 256: return launch_t<256, 4>(pl, p, grid, s);
+    case 128: return launch_t<128, 6>(pl, p, grid, s);
+    case 64: return launch_t<64, 8>(pl, p, grid, s);
+    case 32: return launch_t<32, 8>(pl, p, grid, s);
+  }
+  return fail(OSM_ERR_INVALID, "conv_tc: unsupported BN");
+}
+
+}  // namespace osm

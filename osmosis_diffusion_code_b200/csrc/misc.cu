@@ -1,0 +1,144 @@
+// Small kernels: sinusoidal timestep embedding, the timestep MLP / per-block emb linears, NCHW<->NHWC
+// boundary transposes, conv weight repacking.
+#include "common.cuh"
+
+namespace osm {
+
+// emb[b, j] = cos(t_b f_j) (j < half) | sin(t_b f_{j-half}),  f_j = exp(-ln(1e4) j / half)  (nn.py:103-121)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int dim) {
+  const int b = blockIdx.x, half = dim / 2;
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    // the reference evaluates -log(10000) * arange / half in fp32 (mul then div), then exp, then t * freq
+    const float f = expf(__fdiv_rn(__fmul_rn(-9.210340371976184f, (float)j), (float)half));
+    const float a = __fmul_rn(t[b], f);
+    out[(size_t)b * dim + j] = cosf(a);
+    out[(size_t)b * dim + half + j] = sinf(a);
+  }
+  if ((dim & 1) && threadIdx.x == 0) out[(size_t)b * dim + dim - 1] = 0.f;
+}
+
+int timestep_embedding_launch(const float* t, float* out, int B, int dim, cudaStream_t s) {
+  timestep_embedding_kernel<<<B, 128, 0, s>>>(t, out, dim);
+  OSM_LAUNCH_CHECK("timestep_embedding_kernel");
+  return OSM_OK;
+}
+
+// out[b,n] = bias[n] + sum_k act(in[b,k]) W[n,k].  One warp per output feature n, looping over the batch in
+// chunks of 8 so each weight row is read from HBM once per chunk (weight-bandwidth bound: K*N*4 bytes).
+constexpr int LIN_BCHUNK = 8;
+__global__ void linear_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ W, const float* __restrict__ bias,
+                              float* __restrict__ out, int ld_out, int B, int K, int N, int silu_in) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* wr = W + (size_t)warp * K;
+  for (int b0 = 0; b0 < B; b0 += LIN_BCHUNK) {
+    float acc[LIN_BCHUNK];
+#pragma unroll
+    for (int i = 0; i < LIN_BCHUNK; ++i) acc[i] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+      for (int i = 0; i < LIN_BCHUNK; ++i) {
+        if (b0 + i < B) {
+          float4 v = *reinterpret_cast<const float4*>(in + (size_t)(b0 + i) * ld_in + k);
+          if (silu_in) {
+            v.x = v.x / (1.0f + expf(-v.x)); v.y = v.y / (1.0f + expf(-v.y));
+            v.z = v.z / (1.0f + expf(-v.z)); v.w = v.w / (1.0f + expf(-v.w));
+          }
+          acc[i] += v.x * w4.x + v.y * w4.y + v.z * w4.z + v.w * w4.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LIN_BCHUNK; ++i) {
+      float v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && b0 + i < B) out[(size_t)(b0 + i) * ld_out + warp] = v + (bias ? bias[warp] : 0.f);
+    }
+  }
+}
+
+int linear_launch(const float* in, int ld_in, const float* W, const float* bias, float* out, int ld_out, int B, int K, int N,
+                  int silu_in, cudaStream_t s) {
+  if (K % 4 || ld_in % 4) return fail(OSM_ERR_INVALID, "linear: K and ld_in must be multiples of 4");
+  const int warps_per_block = 8;
+  linear_kernel<<<(N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(in, ld_in, W, bias, out, ld_out, B,
+                                                                                               K, N, silu_in);
+  OSM_LAUNCH_CHECK("linear_kernel");
+  return OSM_OK;
+}
+
+// [B,C,HW] -> [B,HW,Cp] (channels >= C zero-filled)
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int Cp) {
+  const int b = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    float* d = dst + ((size_t)b * HW + p) * Cp;
+    for (int c = 0; c < Cp; c += 4) {
+      float4 v;
+      v.x = (c + 0 < C) ? src[((size_t)b * C + c + 0) * HW + p] : 0.f;
+      v.y = (c + 1 < C) ? src[((size_t)b * C + c + 1) * HW + p] : 0.f;
+      v.z = (c + 2 < C) ? src[((size_t)b * C + c + 2) * HW + p] : 0.f;
+      v.w = (c + 3 < C) ? src[((size_t)b * C + c + 3) * HW + p] : 0.f;
+      *reinterpret_cast<float4*>(d + c) = v;
+    }
+  }
+}
+
+int nchw_to_nhwc_pad_launch(const float* src, float* dst, int B, int C, int HW, int Cp, cudaStream_t s) {
+  int blocks = (HW + 255) / 256;
+  nchw_to_nhwc_pad_kernel<<<dim3(blocks, B), 256, 0, s>>>(src, dst, C, HW, Cp);
+  OSM_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
+  return OSM_OK;
+}
+
+// [B,HW,ld] (first C channels) -> [B,C,HW]
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ld, float* __restrict__ dst, int C, int HW) {
+  const int b = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const float* s = src + ((size_t)b * HW + p) * ld;
+    for (int c = 0; c < C; ++c) dst[((size_t)b * C + c) * HW + p] = s[c];
+  }
+}
+
+int nhwc_to_nchw_launch(const float* src, int ld, float* dst, int B, int C, int HW, cudaStream_t s) {
+  int blocks = (HW + 255) / 256;
+  nhwc_to_nchw_kernel<<<dim3(blocks, B), 256, 0, s>>>(src, ld, dst, C, HW);
+  OSM_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return OSM_OK;
+}
+
+// OIHW (or OI1 for 1x1 / Conv1d) -> forward pack  Wf[tap][co][ci]           (B operand, K-major rows of Cin_p)
+//                                   dgrad pack    Wd[tap'][ci][co], tap' = taps-1-tap   (spatially flipped, transposed)
+// Padded rows/cols are zero.  round_tf32: store the RN-rounded TF32 value so the tensor core's mantissa
+// truncation is exact on the weight operand.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd, int Cout,
+                                        int Cin, int Cout_p, int Cin_p, int taps, int round_tf32) {
+  const size_t total = (size_t)taps * Cout_p * Cin_p;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_p);
+    const int co = (int)((i / Cin_p) % Cout_p);
+    const int tap = (int)(i / ((size_t)Cin_p * Cout_p));
+    float v = 0.f;
+    if (ci < Cin && co < Cout) v = w[((size_t)co * Cin + ci) * taps + tap];
+    if (round_tf32) {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+      v = __uint_as_float(r);
+    }
+    if (wf) wf[i] = v;
+    if (wd) wd[((size_t)(taps - 1 - tap) * Cin_p + ci) * Cout_p + co] = v;
+  }
+}
+
+int pack_conv_weight_launch(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p,
+                            int taps, int round_tf32, cudaStream_t s) {
+  const size_t total = (size_t)taps * Cout_p * Cin_p;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_conv_weight_kernel<<<(unsigned)blocks, 256, 0, s>>>(w_oihw, w_fwd, w_dgrad, Cout, Cin, Cout_p, Cin_p, taps, round_tf32);
+  OSM_LAUNCH_CHECK("pack_conv_weight_kernel");
+  return OSM_OK;
+}
+
+}  // namespace osm

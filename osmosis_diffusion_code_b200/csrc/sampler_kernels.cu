@@ -1,0 +1,391 @@
+// Sampler-side kernels: posterior mean/variance (+VJP), guidance update, unguided DDPM update,
+// measurement operators and the fused phi-optimisation / guidance-gradient loop.
+//
+// All tensors here are NCHW planes [B,C,HW] fp32 (the layout at the reference boundary), so every
+// access is pixel-contiguous and coalesced.  These kernels are HBM/L2-bound; arithmetic is written
+// with explicit __fmul_rn/__fadd_rn where the reference rounds op-by-op so that results track the
+// fp32 oracle to the last bit where possible (no FMA contraction across reference ops).
+#include "common.cuh"
+
+namespace osm {
+
+// ------------------------------------------------------------------------------------------------
+// posterior forward:  x0 = c1*x - c2*eps ; mean = m1*x0 + m2*x ; logvar = frac*maxlog + (1-frac)*minlog
+// (posterior_mean_variance.py:127-136, 246-258)
+// ------------------------------------------------------------------------------------------------
+__global__ void posterior_fwd_kernel(const float* __restrict__ coef, const int32_t* __restrict__ t_idx,
+                                     const float* __restrict__ x, const float* __restrict__ mo, float* __restrict__ x0,
+                                     float* __restrict__ mean, float* __restrict__ logvar, int C, int HW) {
+  const int b = blockIdx.y;
+  const float* cf = coef + 8 * (size_t)t_idx[b];
+  const float c1 = cf[0], c2 = cf[1], m1 = cf[2], m2 = cf[3], maxlog = cf[4], minlog = cf[5];
+  const size_t n4 = (size_t)C * HW / 4;
+  const float4* xv = reinterpret_cast<const float4*>(x + (size_t)b * C * HW);
+  const float4* ev = reinterpret_cast<const float4*>(mo + (size_t)b * 2 * C * HW);
+  const float4* vv = reinterpret_cast<const float4*>(mo + (size_t)b * 2 * C * HW + (size_t)C * HW);
+  float4* x0v = reinterpret_cast<float4*>(x0 + (size_t)b * C * HW);
+  float4* mv = reinterpret_cast<float4*>(mean + (size_t)b * C * HW);
+  float4* lv = reinterpret_cast<float4*>(logvar + (size_t)b * C * HW);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 X = xv[i], E = ev[i], V = vv[i], X0, M, L;
+#define OSM_POST1(f)                                                                      \
+  {                                                                                       \
+    float p0 = __fsub_rn(__fmul_rn(c1, X.f), __fmul_rn(c2, E.f));                         \
+    X0.f = p0;                                                                            \
+    M.f = __fadd_rn(__fmul_rn(m1, p0), __fmul_rn(m2, X.f));                               \
+    float fr = __fdiv_rn(__fadd_rn(V.f, 1.0f), 2.0f);                                     \
+    L.f = __fadd_rn(__fmul_rn(fr, maxlog), __fmul_rn(__fsub_rn(1.0f, fr), minlog));       \
+  }
+    OSM_POST1(x) OSM_POST1(y) OSM_POST1(z) OSM_POST1(w)
+#undef OSM_POST1
+    x0v[i] = X0; mv[i] = M; lv[i] = L;
+  }
+}
+
+int posterior_fwd_launch(const float* coef, const int32_t* t_idx, const float* x, const float* mo, float* x0, float* mean,
+                         float* logvar, int B, int C, int HW, cudaStream_t s) {
+  if ((C * HW) % 4) return fail(OSM_ERR_INVALID, "posterior_fwd: C*HW must be a multiple of 4");
+  int blocks = (int)(((size_t)C * HW / 4 + 255) / 256);
+  if (blocks > 1184) blocks = 1184;  // 8 x 148 SMs, grid-stride
+  posterior_fwd_kernel<<<dim3(blocks, B), 256, 0, s>>>(coef, t_idx, x, mo, x0, mean, logvar, C, HW);
+  OSM_LAUNCH_CHECK("posterior_fwd_kernel");
+  return OSM_OK;
+}
+
+// VJP: g_eps = -c2*(g_x0 + m1*g_mean); g_x = c1*(g_x0 + m1*g_mean) + m2*g_mean; g_v = 0.5*(maxlog-minlog)*g_logvar
+__global__ void posterior_vjp_kernel(const float* __restrict__ coef, const int32_t* __restrict__ t_idx,
+                                     const float* __restrict__ g_x0, const float* __restrict__ g_mean,
+                                     const float* __restrict__ g_logvar, float* __restrict__ g_x,
+                                     float* __restrict__ g_mo, int C, int HW) {
+  const int b = blockIdx.y;
+  const float* cf = coef + 8 * (size_t)t_idx[b];
+  const float c1 = cf[0], c2 = cf[1], m1 = cf[2], m2 = cf[3], dl = 0.5f * (cf[4] - cf[5]);
+  const size_t n = (size_t)C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * n + i;
+    float gm = g_mean ? g_mean[o] : 0.f;
+    float g0 = (g_x0 ? g_x0[o] : 0.f) + m1 * gm;
+    g_x[o] = c1 * g0 + m2 * gm;
+    g_mo[(size_t)b * 2 * n + i] = -c2 * g0;
+    g_mo[(size_t)b * 2 * n + n + i] = g_logvar ? dl * g_logvar[o] : 0.f;
+  }
+}
+
+int posterior_vjp_launch(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean, const float* g_logvar,
+                         float* g_x, float* g_mo, int B, int C, int HW, cudaStream_t s) {
+  int blocks = (int)(((size_t)C * HW + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  posterior_vjp_kernel<<<dim3(blocks, B), 256, 0, s>>>(coef, t_idx, g_x0, g_mean, g_logvar, g_x, g_mo, C, HW);
+  OSM_LAUNCH_CHECK("posterior_vjp_kernel");
+  return OSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_out = mean - scale_c * clamp(g, +-clip) + [t != 0] * exp(0.5*logvar) * noise
+// (condition_methods.py:211-223, gaussian_diffusion.py:266-268)
+// ------------------------------------------------------------------------------------------------
+__global__ void sampler_update_kernel(const float* __restrict__ mean, const float* __restrict__ g_a,
+                                      const float* __restrict__ g_b, const float* __restrict__ scale4, float clip,
+                                      const float* __restrict__ logvar, const float* __restrict__ noise,
+                                      const int32_t* __restrict__ t_idx, float* __restrict__ x_out,
+                                      float* __restrict__ grad_out, int C, int HW) {
+  const int b = blockIdx.y;
+  const bool add_noise = t_idx[b] != 0;
+  const size_t n = (size_t)C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * n + i;
+    const int c = (int)(i / HW);
+    float g = g_a[o];
+    if (g_b) g = __fadd_rn(g, g_b[o]);
+    if (grad_out) grad_out[o] = g;
+    float gc = g;
+    if (clip >= 0.f) gc = fminf(fmaxf(g, -clip), clip);
+    float v = __fsub_rn(mean[o], __fmul_rn(scale4[c], gc));
+    if (add_noise) v = __fadd_rn(v, __fmul_rn(expf(__fmul_rn(0.5f, logvar[o])), noise[o]));
+    x_out[o] = v;
+  }
+}
+
+int sampler_update_launch(const float* mean, const float* g_a, const float* g_b, const float* scale4, float clip,
+                          const float* logvar, const float* noise, const int32_t* t_idx, float* x_out, float* grad_out, int B,
+                          int C, int HW, cudaStream_t s) {
+  int blocks = (int)(((size_t)C * HW + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  sampler_update_kernel<<<dim3(blocks, B), 256, 0, s>>>(mean, g_a, g_b, scale4, clip, logvar, noise, t_idx, x_out, grad_out,
+                                                        C, HW);
+  OSM_LAUNCH_CHECK("sampler_update_kernel");
+  return OSM_OK;
+}
+
+// x = c_x * (x - c_eps * eps) + c_z * z      (osmosis_utils/diffusion.py:122)
+__global__ void ddpm_uncond_kernel(float* __restrict__ x, const float* __restrict__ mo, const float* __restrict__ z, float c_x,
+                                   float c_eps, float c_z, int C, int Cmo, int HW) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)C * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * n + i;
+    float e = mo[(size_t)b * Cmo * HW + i];
+    float v = __fmul_rn(c_x, __fsub_rn(x[o], __fmul_rn(c_eps, e)));
+    x[o] = __fadd_rn(v, __fmul_rn(c_z, z[o]));
+  }
+}
+
+int ddpm_uncond_launch(float* x, const float* mo, const float* z, float c_x, float c_eps, float c_z, int B, int C, int Cmo,
+                       int HW, cudaStream_t s) {
+  int blocks = (int)(((size_t)C * HW + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  ddpm_uncond_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, mo, z, c_x, c_eps, c_z, C, Cmo, HW);
+  OSM_LAUNCH_CHECK("ddpm_uncond_kernel");
+  return OSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement operator  uw_c = J_c e^{-phi_a,c d} + phi_inf,c (1 - e^{-phi_b,c d})
+// ------------------------------------------------------------------------------------------------
+struct DepthFn {
+  int kind;
+  float v0, v1, v2;
+};
+
+__device__ __forceinline__ float depth_convert(const DepthFn& f, float d) {
+  if (f.kind == OSM_DEPTH_GAMMA) {
+    float base = __fmul_rn(__fadd_rn(d, f.v0), f.v1);
+    return (f.v2 == 1.0f) ? base : powf(base, f.v2);
+  }
+  if (f.kind == OSM_DEPTH_MOVE) return __fadd_rn(d, f.v0);
+  return __fmul_rn(0.5f, __fadd_rn(d, 1.0f));
+}
+// d(depth_convert)/d(d)
+__device__ __forceinline__ float depth_slope(const DepthFn& f, float d) {
+  if (f.kind == OSM_DEPTH_GAMMA) {
+    if (f.v2 == 1.0f) return f.v1;
+    float base = (d + f.v0) * f.v1;
+    return f.v2 * f.v1 * powf(base, f.v2 - 1.0f);
+  }
+  if (f.kind == OSM_DEPTH_MOVE) return 1.0f;
+  return 0.5f;
+}
+
+struct Phi9 {
+  float a[3], b[3], inf[3];
+};
+__device__ __forceinline__ Phi9 load_phi(int op_kind, const float* __restrict__ phi) {
+  Phi9 p;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    p.a[c] = (op_kind == OSM_OP_HAZE) ? phi[0] : phi[c];
+    p.b[c] = (op_kind == OSM_OP_UNDERWATER_REVISED) ? phi[3 + c] : p.a[c];
+    p.inf[c] = phi[6 + c];
+  }
+  return p;
+}
+
+__global__ void operator_fwd_kernel(int op_kind, DepthFn df, const float* __restrict__ x, const float* __restrict__ phi,
+                                    float* __restrict__ out, int HW) {
+  const int b = blockIdx.y;
+  const Phi9 p = load_phi(op_kind, phi + 9 * b);
+  const float* xb = x + (size_t)b * 4 * HW;
+  float* ob = out + (size_t)b * 3 * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float d = depth_convert(df, xb[3 * (size_t)HW + i]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float J = __fmul_rn(0.5f, __fadd_rn(xb[c * (size_t)HW + i], 1.0f));
+      const float ea = expf(__fmul_rn(-p.a[c], d));
+      const float eb = expf(__fmul_rn(-p.b[c], d));
+      ob[c * (size_t)HW + i] = __fadd_rn(__fmul_rn(J, ea), __fmul_rn(p.inf[c], __fsub_rn(1.0f, eb)));
+    }
+  }
+}
+
+int operator_fwd_launch(int op_kind, int depth_kind, const float* dv, const float* x, const float* phi, float* out, int B,
+                        int HW, cudaStream_t s) {
+  DepthFn df{depth_kind, dv[0], dv[1], dv[2]};
+  int blocks = (HW + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  operator_fwd_kernel<<<dim3(blocks, B), 256, 0, s>>>(op_kind, df, x, phi, out, HW);
+  OSM_LAUNCH_CHECK("operator_fwd_kernel");
+  return OSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused guidance / phi-optimisation loop.  One CTA per image (512 threads); the image's 7 planes
+// (x0 RGBD + y RGB, 1.8 MB at 256x256) stay L2-resident across the n_iter passes.
+//
+// Per evaluation:
+//   r_c = (y_c - (2 uw_c - 1)) w ;  L = ||r||_2 ;  dL/dphi = (1/L) sum_pix r_c * d r_c/d phi
+//   phi <- phi - eta * dL/dphi     (aux losses do not depend on phi)
+// Last evaluation additionally writes d(L + aux)/d x0 using phi BEFORE that evaluation's update.
+// ------------------------------------------------------------------------------------------------
+constexpr int GUID_THREADS = 512;
+constexpr int GUID_NRED = 10;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of NV doubles per thread; result broadcast to all threads via smem `red` [NV]
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* red /*[32*NV + NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) red[warp * NV + k] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = (lane < (int)(blockDim.x >> 5)) ? red[lane * NV + k] : 0.0;
+      s = warp_sum(s);
+      if (lane == 0) red[32 * NV + k] = s;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = red[32 * NV + k];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GUID_THREADS, 1)
+guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, const float* __restrict__ y,
+                         float* __restrict__ phi_io, const int32_t* __restrict__ freeze_flag, float* __restrict__ g_x0,
+                         float* __restrict__ losses, int HW) {
+  __shared__ double red[32 * GUID_NRED + GUID_NRED];
+  __shared__ float sphi[9];
+  const int b = blockIdx.x;
+  const float* xb = x0 + (size_t)b * 4 * HW;
+  const float* yb = y + (size_t)b * 3 * HW;
+  float* gb = g_x0 + (size_t)b * 4 * HW;
+  const DepthFn df{P.depth_kind, P.depth_val[0], P.depth_val[1], P.depth_val[2]};
+  const DepthFn wf{P.weight_depth_kind, P.weight_val[0], P.weight_val[1], P.weight_val[2]};
+  const bool freeze = freeze_flag[0] != 0;
+  const int n_eval = freeze ? 1 : P.n_iter;
+  if (threadIdx.x < 9) sphi[threadIdx.x] = phi_io[9 * b + threadIdx.x];
+
+  // phi-independent reductions: channel means (avrg_loss) and the val_loss sum
+  double pre[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = xb[c * (size_t)HW + i];
+      pre[c] += v;
+      const float e = fmaxf(fabsf(v) - 0.7f, 0.f);
+      pre[3] += (double)(e * e);
+    }
+  }
+  block_sum<4>(pre, red);
+  float mean_c[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) mean_c[c] = (float)(pre[c] / HW);
+  const float avrg_term = fabsf(mean_c[0]) + fabsf(mean_c[1]) + fabsf(mean_c[2]);
+  const float val_term = (float)(pre[3] / (3.0 * HW));
+
+  float Lnorm = 0.f;
+  for (int it = 0; it < n_eval; ++it) {
+    const bool last = (it == n_eval - 1);
+    const Phi9 p = load_phi(P.op_kind, sphi);
+    double acc[GUID_NRED];
+#pragma unroll
+    for (int k = 0; k < GUID_NRED; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+      const float xd = xb[3 * (size_t)HW + i];
+      const float d = depth_convert(df, xd);
+      const float w = P.weight_kind ? depth_convert(wf, xd) : 1.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float J = __fmul_rn(0.5f, __fadd_rn(xb[c * (size_t)HW + i], 1.0f));
+        const float ea = expf(__fmul_rn(-p.a[c], d));
+        const float eb = expf(__fmul_rn(-p.b[c], d));
+        const float uw = __fadd_rn(__fmul_rn(J, ea), __fmul_rn(p.inf[c], __fsub_rn(1.0f, eb)));
+        const float deg = __fsub_rn(__fmul_rn(2.0f, uw), 1.0f);
+        const float r = __fmul_rn(__fsub_rn(yb[c * (size_t)HW + i], deg), w);
+        acc[0] += (double)r * (double)r;
+        // un-normalised dL/duw = -2 w r ;  duw/dphi_a = -d J ea ; duw/dphi_b = phi_inf d eb ; duw/dphi_inf = 1 - eb
+        const float gu = -2.0f * w * r;
+        acc[1 + c] += (double)(gu * (-d * J * ea));
+        acc[4 + c] += (double)(gu * (p.inf[c] * d * eb));
+        acc[7 + c] += (double)(gu * (1.0f - eb));
+      }
+    }
+    block_sum<GUID_NRED>(acc, red);
+    Lnorm = (float)sqrt(acc[0]);
+    const float invL = 1.0f / Lnorm;
+
+    if (last) {
+      // d total / d x0 at the current phi (before this evaluation's SGD step)
+      const float ka = P.gamma_avrg / (float)HW;
+      const float kv = P.gamma_val * 2.0f / (3.0f * (float)HW);
+      for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+        const float xd = xb[3 * (size_t)HW + i];
+        const float d = depth_convert(df, xd);
+        const float w = P.weight_kind ? depth_convert(wf, xd) : 1.0f;
+        float gd = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float xc = xb[c * (size_t)HW + i];
+          const float J = __fmul_rn(0.5f, __fadd_rn(xc, 1.0f));
+          const float ea = expf(__fmul_rn(-p.a[c], d));
+          const float eb = expf(__fmul_rn(-p.b[c], d));
+          const float uw = __fadd_rn(__fmul_rn(J, ea), __fmul_rn(p.inf[c], __fsub_rn(1.0f, eb)));
+          const float deg = __fsub_rn(__fmul_rn(2.0f, uw), 1.0f);
+          const float r = __fmul_rn(__fsub_rn(yb[c * (size_t)HW + i], deg), w);
+          const float guw = -2.0f * w * r * invL;
+          float g = 0.5f * guw * ea;
+          const float sgn_m = (mean_c[c] > 0.f) ? 1.f : ((mean_c[c] < 0.f) ? -1.f : 0.f);
+          g += ka * sgn_m;
+          const float ex = fmaxf(fabsf(xc) - 0.7f, 0.f);
+          g += kv * ex * ((xc > 0.f) ? 1.f : ((xc < 0.f) ? -1.f : 0.f));
+          gb[c * (size_t)HW + i] = g;
+          gd += guw * (-p.a[c] * J * ea + p.inf[c] * p.b[c] * eb);
+        }
+        gb[3 * (size_t)HW + i] = gd * depth_slope(df, xd);
+      }
+    }
+    if (!freeze) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        // SGD per group (measurements.py:266-303 / torch.optim.SGD, no momentum)
+        if (P.op_kind == OSM_OP_UNDERWATER_REVISED) {
+          for (int c = 0; c < 3; ++c) {
+            sphi[c] -= P.eta[0] * (float)(acc[1 + c] * invL);
+            sphi[3 + c] -= P.eta[1] * (float)(acc[4 + c] * invL);
+            sphi[6 + c] -= P.eta[2] * (float)(acc[7 + c] * invL);
+          }
+        } else if (P.op_kind == OSM_OP_UNDERWATER) {
+          for (int c = 0; c < 3; ++c) {
+            sphi[c] -= P.eta[0] * (float)((acc[1 + c] + acc[4 + c]) * invL);
+            sphi[6 + c] -= P.eta[1] * (float)(acc[7 + c] * invL);
+          }
+        } else {
+          double s = 0;
+          for (int c = 0; c < 3; ++c) s += acc[1 + c] + acc[4 + c];
+          sphi[0] -= P.eta[0] * (float)(s * invL);
+          for (int c = 0; c < 3; ++c) sphi[6 + c] -= P.eta[1] * (float)(acc[7 + c] * invL);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < 9) phi_io[9 * b + threadIdx.x] = sphi[threadIdx.x];
+  if (threadIdx.x == 0) {
+    losses[4 * b + 0] = Lnorm;
+    losses[4 * b + 1] = avrg_term;
+    losses[4 * b + 2] = val_term;
+    losses[4 * b + 3] = Lnorm + P.gamma_avrg * avrg_term + P.gamma_val * val_term;
+  }
+}
+
+int guidance_phi_loop_launch(const osm_guidance_params* p, const float* x0, const float* y, float* phi,
+                             const int32_t* freeze_flag, float* g_x0, float* losses, int B, int HW, cudaStream_t s) {
+  if (p->op_kind < 0 || p->op_kind > 2) return fail(OSM_ERR_INVALID, "guidance: unknown operator kind");
+  if (p->n_iter < 1) return fail(OSM_ERR_INVALID, "guidance: n_iter must be >= 1");
+  guidance_phi_loop_kernel<<<B, GUID_THREADS, 0, s>>>(*p, x0, y, phi, freeze_flag, g_x0, losses, HW);
+  OSM_LAUNCH_CHECK("guidance_phi_loop_kernel");
+  return OSM_OK;
+}
+
+}  // namespace osm

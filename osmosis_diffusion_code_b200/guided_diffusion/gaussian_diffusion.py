@@ -1,0 +1,330 @@
+"""Samplers: schedule tables, timestep respacing and the guided reverse loop.
+
+Mirrors the reference `guided_diffusion/gaussian_diffusion.py`: the sampler registry and `create_sampler`
+(:19-62), `GaussianDiffusion` (:65-365), `space_timesteps` (:373-426), `SpacedDiffusion` / `_WrappedModel`
+(:429-489), `DDPM` (:492-503), `get_named_beta_schedule` (:542-566), `extract_and_expand` (:593-597).
+
+`p_sample_loop` keeps the reference's signature and return value `(img, variable_dict, loss, pred_xstart on
+CPU)`.  Two execution paths produce the same arithmetic:
+
+  * fused (default when the model is the native UNet and the conditioning method is the native `osmosis`
+    one): per step  UNet forward -> posterior kernel -> guidance/phi kernel -> posterior VJP -> UNet input-VJP
+    -> sampler-update kernel, all asynchronous on the current stream with no host synchronisation; the step
+    index and the freeze flag live in device memory so the launch sequence is identical every step.
+  * autograd-compatible (any other model / conditioning callable): the reference's call sequence
+    (`p_mean_variance` -> `measurement_cond_fn(...)` -> noise), differentiable through autograd Functions.
+
+Deliberate deviations: batches of B > 1 run as B independent chains instead of crashing
+(:216); no per-step `.item()` / `.cpu()` (the tqdm postfix of :276-296) - loss and phi are read once at the end.
+The dead `q_sample(measurement)` draw (:241) IS mirrored because it advances the RNG stream.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import lib as _lib
+from ..osmosis_utils import utils as utilso
+from .posterior_mean_variance import PosteriorFn, get_mean_processor, get_var_processor
+
+__SAMPLER__ = {}
+
+
+def register_sampler(name: str):
+    def wrapper(cls):
+        if __SAMPLER__.get(name, None):
+            raise NameError(f"Name {name} is already registered!")
+        __SAMPLER__[name] = cls
+        return cls
+    return wrapper
+
+
+def get_sampler(name: str):
+    if __SAMPLER__.get(name, None) is None:
+        raise NameError(f"Name {name} is not defined!")
+    return __SAMPLER__[name]
+
+
+def create_sampler(sampler, steps, noise_schedule, model_mean_type, model_var_type, dynamic_threshold, clip_denoised,
+                   rescale_timesteps, timestep_respacing="", **kwargs):
+    cls = get_sampler(name=sampler)
+    betas = get_named_beta_schedule(noise_schedule, steps)
+    if not timestep_respacing:
+        timestep_respacing = [steps]
+    return cls(use_timesteps=space_timesteps(steps, timestep_respacing), betas=betas, model_mean_type=model_mean_type,
+               model_var_type=model_var_type, dynamic_threshold=dynamic_threshold, clip_denoised=clip_denoised,
+               rescale_timesteps=rescale_timesteps, annealing_time=kwargs.get("annealing_time", False))
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps):
+    if schedule_name == "linear":
+        scale = 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    if schedule_name == "cosine":
+        abar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        n = num_diffusion_timesteps
+        return np.array([min(1 - abar((i + 1) / n) / abar(i / n), 0.999) for i in range(n)])
+    raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+
+def space_timesteps(num_timesteps, section_counts):
+    """Which original timesteps a respaced chain keeps: "ddimN", "a,b,c" per-section counts, or an int."""
+    if isinstance(section_counts, str):
+        if section_counts.startswith("ddim"):
+            desired = int(section_counts[len("ddim"):])
+            for stride in range(1, num_timesteps):
+                if len(range(0, num_timesteps, stride)) == desired:
+                    return set(range(0, num_timesteps, stride))
+            raise ValueError(f"cannot create exactly {num_timesteps} steps with an integer stride")
+        section_counts = [int(x) for x in section_counts.split(",")]
+    elif isinstance(section_counts, int):
+        section_counts = [section_counts]
+    base, extra = divmod(num_timesteps, len(section_counts))
+    kept, start = [], 0
+    for i, count in enumerate(section_counts):
+        size = base + (1 if i < extra else 0)
+        if size < count:
+            raise ValueError(f"cannot divide section of {size} steps into {count}")
+        stride = 1 if count <= 1 else (size - 1) / (count - 1)
+        pos = 0.0
+        for _ in range(count):
+            kept.append(start + round(pos))
+            pos += stride
+        start += size
+    return set(kept)
+
+
+def extract_and_expand(array, time, target):
+    array = torch.from_numpy(np.asarray(array)).to(target.device)[time].float()
+    while array.ndim < target.ndim:
+        array = array.unsqueeze(-1)
+    return array.expand_as(target)
+
+
+class GaussianDiffusion:
+    def __init__(self, betas, model_mean_type, model_var_type, dynamic_threshold, clip_denoised, rescale_timesteps, **kwargs):
+        betas = np.array(betas, dtype=np.float64)
+        assert betas.ndim == 1, "betas must be 1-D"
+        assert (0 < betas).all() and (betas <= 1).all(), "betas must be in (0..1]"
+        self.betas = betas
+        self.num_timesteps = int(betas.shape[0])
+        self.rescale_timesteps = rescale_timesteps
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self.mean_processor = get_mean_processor(model_mean_type, betas=betas, dynamic_threshold=dynamic_threshold,
+                                                 clip_denoised=clip_denoised)
+        self.var_processor = get_var_processor(model_var_type, betas=betas)
+
+    # ---- pieces of the reference API --------------------------------------------------------------------
+    def q_sample(self, x_start, t):
+        """sqrt(abar_t) x + sqrt(1 - abar_t) randn - the osmosis path only needs its RNG side effect (:241)."""
+        noise = torch.randn_like(x_start)
+        c1 = extract_and_expand(self.sqrt_alphas_cumprod, t, x_start)
+        c2 = extract_and_expand(self.sqrt_one_minus_alphas_cumprod, t, x_start)
+        return c1 * x_start + c2 * noise
+
+    def _scale_timesteps(self, t):
+        if self.rescale_timesteps:
+            return t.float() * (1000.0 / self.num_timesteps)
+        return t
+
+    def p_mean_variance(self, model, x, t):
+        model_output = model(x, self._scale_timesteps(t))
+        if model_output.shape[1] != 2 * x.shape[1]:
+            raise NotImplementedError("the native posterior kernel expects a learned-variance model (2C output channels)")
+        coef = self.mean_processor.table.on(x.device)
+        x0, mean, logvar = PosteriorFn.apply(x, model_output, coef, t.to(torch.int32).contiguous())
+        return {"mean": mean, "variance": torch.exp(logvar.detach()), "log_variance": logvar, "pred_xstart": x0}
+
+    def p_sample(self, model, x, t):
+        raise NotImplementedError
+
+    # ---- the loop ---------------------------------------------------------------------------------------
+    def _model_timestep(self, idx):
+        return float(idx) * (1000.0 / self.num_timesteps) if self.rescale_timesteps else float(idx)
+
+    def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record, save_root, pretrain_model=None,
+                      image_idx=None, record_every=150, rgb_guidance=False, sample_pattern=None, **kwargs):
+        if pretrain_model != "osmosis" or rgb_guidance:
+            raise NotImplementedError("only the osmosis guided path (pretrain_model='osmosis', rgb_guidance=False) is native")
+        if not x_start.is_cuda:
+            raise _lib.OsmError("p_sample_loop needs CUDA tensors (no CPU fallback)")
+        from .condition_methods import PosteriorSamplingOsmosis
+        from .unet import UNetModel
+        cond = getattr(measurement_cond_fn, "__self__", None)
+        fused = (isinstance(model, UNetModel) and isinstance(cond, PosteriorSamplingOsmosis)
+                 and getattr(measurement_cond_fn, "__func__", None) is PosteriorSamplingOsmosis.conditioning
+                 and kwargs.get("fused", True))
+        steps = kwargs.get("max_steps", None)  # truncation hook used by benchmarks / tests; None = full chain
+        noise_mode = kwargs.get("noise_mode", "batch")  # 'batch': randn_like(img) as the reference; 'shared': one draw per step
+        idxs = list(range(self.num_timesteps))[::-1]
+        if steps is not None:
+            idxs = idxs[:steps]
+        if fused:
+            return self._loop_fused(model, cond, x_start, measurement, sample_pattern, idxs, noise_mode)
+        return self._loop_autograd(model, measurement_cond_fn, x_start, measurement, sample_pattern, idxs)
+
+    def _draw(self, like, noise_mode):
+        if noise_mode == "shared":
+            return torch.randn((1,) + tuple(like.shape[1:]), device=like.device, dtype=like.dtype).expand_as(like).contiguous()
+        return torch.randn_like(like)
+
+    def _guidance_on(self, sample_pattern, idx):
+        return (sample_pattern["pattern"] == "original") or (sample_pattern["pattern"] is None) or \
+            (sample_pattern["start_guidance"] * self.num_timesteps >= idx >= sample_pattern["stop_guidance"] * self.num_timesteps)
+
+    def fused_state(self, model, cond, x, measurement):
+        """Device-resident buffers of the fused step (allocated once per loop)."""
+        B, Cc, H, W = x.shape
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        return dict(
+            coef=self.mean_processor.table.on(dev), t_idx=torch.zeros(B, dtype=torch.int32, device=dev),
+            t_model=torch.zeros(B, **f32), freeze=torch.zeros(1, dtype=torch.int32, device=dev),
+            model_out=torch.empty(B, 2 * Cc, H, W, **f32), x0=torch.empty(B, Cc, H, W, **f32),
+            mean=torch.empty(B, Cc, H, W, **f32), logvar=torch.empty(B, Cc, H, W, **f32),
+            g_x0=torch.empty(B, Cc, H, W, **f32), g_direct=torch.empty(B, Cc, H, W, **f32),
+            g_mo=torch.empty(B, 2 * Cc, H, W, **f32), g_unet=torch.empty(B, Cc, H, W, **f32),
+            grad=torch.empty(B, Cc, H, W, **f32), losses=torch.zeros(B, 4, **f32),
+            scale=cond._scale4(Cc).to(dev), y=measurement.contiguous().float(),
+            clip=(cond.gradient_clip_value if cond.gradient_clip else -1.0))
+
+    def fused_step(self, model, cond, st, img, noise):
+        """One guided reverse step on device buffers; `img` is updated in place.  No host synchronisation."""
+        L = _lib.load()
+        B, Cc, H, W = img.shape
+        HW = H * W
+        s = _lib.stream()
+        model._forward_raw(img, st["t_model"], out=st["model_out"])
+        _lib.check(L.osm_posterior_fwd(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
+                                       _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, s))
+        cond.guidance_gradient(st["x0"], st["y"], st["freeze"], st["g_x0"], st["losses"])
+        _lib.check(L.osm_posterior_vjp(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(st["g_x0"]), None, None,
+                                       _lib.ptr(st["g_direct"]), _lib.ptr(st["g_mo"]), B, Cc, HW, s))
+        model._vjp_raw(st["g_mo"], grad_x=st["g_unet"])
+        _lib.check(L.osm_sampler_update(_lib.ptr(st["mean"]), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
+                                        _lib.ptr(st["scale"]), st["clip"], _lib.ptr(st["logvar"]), _lib.ptr(noise),
+                                        _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["grad"]), B, Cc, HW, s))
+
+    def _loop_fused(self, model, cond, x_start, measurement, sample_pattern, idxs, noise_mode):
+        img = x_start.detach().clone().contiguous().float()
+        st = self.fused_state(model, cond, img, measurement)
+        op = cond.operator
+        for idx in idxs:
+            if not self._guidance_on(sample_pattern, idx):
+                raise NotImplementedError("unguided steps inside the guided loop are not on the native path")
+            if utilso.set_alternate_length(sample_pattern, idx, self.num_timesteps) != 1:
+                raise NotImplementedError("local_M > 1 is not on the native path")
+            freeze = utilso.is_freeze_phi(sample_pattern, idx, self.num_timesteps)
+            st["t_idx"].fill_(idx)
+            st["t_model"].fill_(self._model_timestep(idx))
+            st["freeze"].fill_(1 if freeze else 0)
+            op.set_variable_gradients(value=not freeze)
+            self._draw(st["y"], noise_mode)            # dead q_sample draw: RNG parity with :241
+            noise = self._draw(img, noise_mode)        # drawn even at t = 0 (:266)
+            self.fused_step(model, cond, st, img, noise)
+        variable_dict = op.optimize(freeze_phi=True)
+        loss = st["losses"][:, 0].cpu().numpy()
+        self.last_gradients = st["grad"]
+        self.last_aux = st["losses"]
+        return img, variable_dict, loss, st["x0"].detach().cpu()
+
+    def _loop_autograd(self, model, measurement_cond_fn, x_start, measurement, sample_pattern, idxs):
+        img = x_start
+        device = img.device
+        loss, variable_dict, out = None, {}, None
+        for idx in idxs:
+            time = torch.tensor([idx] * img.shape[0], device=device)
+            guidance = self._guidance_on(sample_pattern, idx)
+            for _ in range(utilso.set_alternate_length(sample_pattern, idx, self.num_timesteps)):
+                img.requires_grad_(bool(guidance))
+                out = self.p_mean_variance(model=model, x=img, t=time)
+                out["sample"] = out["mean"]
+                noisy_measurement = self.q_sample(measurement, t=time)
+                freeze = utilso.is_freeze_phi(sample_pattern, idx, self.num_timesteps)
+                if guidance:
+                    img, loss, variable_dict, _grads, _aux = measurement_cond_fn(
+                        x_t=out["sample"], measurement=measurement, noisy_measurement=noisy_measurement, x_prev=img,
+                        x_0_hat=out["pred_xstart"], freeze_phi=freeze, time_index=float(idx) / self.num_timesteps)
+                else:
+                    img = out["sample"]
+                noise = torch.randn_like(img)
+                img = img.detach()
+                if idx != 0:
+                    img = img + torch.exp(0.5 * out["log_variance"].detach()) * noise
+        return img, variable_dict, loss, out["pred_xstart"].detach().cpu()
+
+
+class SpacedDiffusion(GaussianDiffusion):
+    """A diffusion process that keeps a subset of the base process' timesteps (betas re-derived from abar)."""
+
+    def __init__(self, use_timesteps, **kwargs):
+        self.use_timesteps = set(use_timesteps)
+        self.timestep_map = []
+        self.original_num_steps = len(kwargs["betas"])
+        base_abar = np.cumprod(1.0 - np.array(kwargs["betas"], dtype=np.float64), axis=0)
+        last, new_betas = 1.0, []
+        for i, abar in enumerate(base_abar):
+            if i in self.use_timesteps:
+                new_betas.append(1 - abar / last)
+                last = abar
+                self.timestep_map.append(i)
+        kwargs["betas"] = np.array(new_betas)
+        super().__init__(**kwargs)
+
+    def p_mean_variance(self, model, *args, **kwargs):
+        return super().p_mean_variance(self._wrap_model(model), *args, **kwargs)
+
+    def _wrap_model(self, model):
+        if isinstance(model, _WrappedModel):
+            return model
+        return _WrappedModel(model, self.timestep_map, self.rescale_timesteps, self.original_num_steps)
+
+    def _scale_timesteps(self, t):
+        return t  # done by the wrapped model
+
+    def _model_timestep(self, idx):
+        t = float(self.timestep_map[idx])
+        return t * (1000.0 / self.original_num_steps) if self.rescale_timesteps else t
+
+
+class _WrappedModel:
+    def __init__(self, model, timestep_map, rescale_timesteps, original_num_steps):
+        self.model = model
+        self.timestep_map = timestep_map
+        self.rescale_timesteps = rescale_timesteps
+        self.original_num_steps = original_num_steps
+        self._map = {}
+
+    def __call__(self, x, ts, **kwargs):
+        key = (str(ts.device), ts.dtype)
+        if key not in self._map:
+            self._map[key] = torch.tensor(self.timestep_map, device=ts.device, dtype=ts.dtype)
+        new_ts = self._map[key][ts]
+        if self.rescale_timesteps:
+            new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
+        return self.model(x, new_ts, **kwargs)
+
+
+@register_sampler(name="ddpm")
+class DDPM(SpacedDiffusion):
+    def p_sample(self, model, x, t):
+        out = self.p_mean_variance(model, x, t)
+        sample = out["mean"]
+        noise = torch.randn_like(x)
+        if t[0] != 0:
+            sample = sample + torch.exp(0.5 * out["log_variance"]) * noise
+        return {"sample": sample, "pred_xstart": out["pred_xstart"]}

@@ -1,0 +1,222 @@
+"""GPU parity tests of the individual kernels, through the C ABI, against the CPU oracle / torch-CPU fp32.
+
+Tolerances (normalised max error = max|a-b| / max|b|):
+  * fp32 kernels (GroupNorm, attention, sampler, guidance, CUDA-core conv): 2e-5 - summation order only.
+  * tcgen05 TF32 conv: 2e-3 - TF32 keeps 10 mantissa bits (what cuDNN does for the reference on a GPU).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import osmosis_oracle as orc
+from osmosis_diffusion_code_b200 import lib as L_
+from tests.helpers import rel_err, maxdiff
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32_TOL = 2e-5
+TF32_TOL = 2e-3
+
+
+def lib():
+    return L_.load()
+
+
+def nhwc(x):  # [B,C,H,W] cpu -> [B,H,W,C] cuda contiguous
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+
+def nchw(x):  # [B,H,W,C] cuda -> [B,C,H,W] cpu
+    return x.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def pack_weight(w, taps, round_tf32):
+    cout, cin = w.shape[:2]
+    cout_p, cin_p = (cout + 31) // 32 * 32, (cin + 31) // 32 * 32
+    wf = torch.zeros(taps * cout_p * cin_p, device=DEV)
+    wd = torch.zeros(taps * cout_p * cin_p, device=DEV)
+    wdev = w.contiguous().to(DEV)
+    L_.check(lib().osm_dbg_pack_conv_weight(L_.ptr(wdev), L_.ptr(wf), L_.ptr(wd), cout, cin, cout_p, cin_p, taps,
+                                            int(round_tf32), L_.stream()))
+    return wf, wd, cout_p, cin_p
+
+
+def run_conv(mode, x_nhwc, ldx, wp, bias, res, ldr, res_mode, out, ldo, acc, B, H, W, cin_p, cout_p, taps):
+    L_.check(lib().osm_dbg_conv(mode, L_.ptr(x_nhwc), ldx, L_.ptr(wp), L_.ptr(bias), L_.ptr(res), ldr, res_mode, L_.ptr(out),
+                                ldo, acc, B, H, W, cin_p, cout_p, taps, L_.stream()))
+    torch.cuda.synchronize()
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, taps
+    (2, 16, 16, 64, 64, 9),
+    (1, 32, 32, 256, 256, 9),
+    (3, 8, 8, 128, 512, 9),
+    (2, 16, 16, 96, 32, 1),
+    (1, 8, 8, 512, 1536, 1),
+    (2, 4, 4, 256, 256, 9),
+    (1, 32, 16, 32, 8, 9),
+    (2, 64, 64, 4, 256, 9),
+]
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["fp32", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_conv_forward_and_dgrad(mode, case):
+    B, H, W, cin, cout, taps = case
+    g = torch.Generator().manual_seed(hash(case) % 2**31)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * taps)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    wf, wd, cout_p, cin_p = pack_weight(w, taps, round_tf32=(mode == 0))
+    xp = torch.zeros(B, H, W, cin_p, device=DEV); xp[..., :cin] = nhwc(x)
+    bp = torch.zeros(cout_p, device=DEV); bp[:cout] = b.to(DEV)
+    out = torch.full((B, H, W, cout_p), float("nan"), device=DEV)
+    run_conv(mode, xp, cin_p, wf, bp, None, 0, 0, out, cout_p, 0, B, H, W, cin_p, cout_p, taps)
+    tol = FP32_TOL if mode == 1 else TF32_TOL
+    got = nchw(out)
+    assert torch.isfinite(got).all()
+    assert rel_err(got[:, :cout], ref) < tol
+    assert float(got[:, cout:].abs().max()) == 0.0 if cout_p > cout else True
+    # input gradient = conv with the flipped / transposed pack
+    gy = torch.randn(B, cout, H, W, generator=g)
+    gref = torch.autograd.grad(F.conv2d(x.requires_grad_(True), w, b, padding=k // 2), x, gy)[0]
+    gyp = torch.zeros(B, H, W, cout_p, device=DEV); gyp[..., :cout] = nhwc(gy)
+    gx = torch.full((B, H, W, cin_p), float("nan"), device=DEV)
+    run_conv(mode, gyp, cout_p, wd, None, None, 0, 0, gx, cin_p, 0, B, H, W, cout_p, cin_p, taps)
+    assert rel_err(nchw(gx)[:, :cin], gref) < tol
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["fp32", "tcgen05"])
+def test_conv_views_residual_accumulate(mode):
+    """Strided input / output views (the skip-concat aliasing), the three residual modes and `+=`."""
+    B, H, W, cin, cout = 2, 16, 16, 64, 128
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(x, w, b, padding=1)
+    wf, _, cout_p, cin_p = pack_weight(w, 9, round_tf32=(mode == 0))
+    tol = FP32_TOL if mode == 1 else TF32_TOL
+    # input is channels [32, 96) of a 160-wide buffer; output is channels [64, 192) of a 256-wide buffer
+    xbuf = torch.randn(B, H, W, 160, generator=g).to(DEV); xbuf[..., 32:96] = nhwc(x)
+    obuf = torch.zeros(B, H, W, 256, device=DEV)
+    bdev = b.to(DEV)
+    res_same = torch.randn(B, cout, H, W, generator=g)
+    res_fine = torch.randn(B, cout, 2 * H, 2 * W, generator=g)
+    res_coarse = torch.randn(B, cout, H // 2, W // 2, generator=g)
+    for res_mode, res, want in ((1, res_same, ref + res_same), (2, res_fine, ref + F.avg_pool2d(res_fine, 2, 2)),
+                                (3, res_coarse, ref + F.interpolate(res_coarse, scale_factor=2, mode="nearest"))):
+        obuf.zero_()
+        r = nhwc(res)
+        L_.check(lib().osm_dbg_conv(mode, C.c_void_p(xbuf.data_ptr() + 32 * 4), 160, L_.ptr(wf), L_.ptr(bdev), L_.ptr(r), cout,
+                                    res_mode, C.c_void_p(obuf.data_ptr() + 64 * 4), 256, 0, B, H, W, cin_p, cout_p, 9, L_.stream()))
+        torch.cuda.synchronize()
+        assert rel_err(nchw(obuf)[:, 64:192], want) < tol
+        assert float(obuf[..., :64].abs().max()) == 0.0 and float(obuf[..., 192:].abs().max()) == 0.0
+    # accumulate
+    prev = torch.randn(B, cout, H, W, generator=g)
+    obuf.zero_(); obuf[..., 64:192] = nhwc(prev)
+    L_.check(lib().osm_dbg_conv(mode, C.c_void_p(xbuf.data_ptr() + 32 * 4), 160, L_.ptr(wf), L_.ptr(bdev), None, 0, 0,
+                                C.c_void_p(obuf.data_ptr() + 64 * 4), 256, 1, B, H, W, cin_p, cout_p, 9, L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(obuf)[:, 64:192], ref + prev) < tol
+
+
+GN_CASES = [
+    # B, H, W, C, silu, modulate, resample
+    (2, 16, 16, 256, 1, 0, 0),
+    (2, 16, 16, 256, 1, 1, 0),
+    (1, 32, 32, 768, 1, 0, 1),
+    (2, 8, 8, 512, 1, 0, 2),
+    (3, 8, 8, 1536, 0, 0, 0),
+    (1, 4, 4, 2048, 1, 1, 0),
+    (2, 64, 64, 128, 1, 0, 0),
+]
+
+
+def _gn_ref(x, gamma, beta, ss, silu, resample):
+    y = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    if ss is not None:
+        C_ = x.shape[1]
+        y = y * (1 + ss[:, :C_, None, None]) + ss[:, C_:2 * C_, None, None]
+    if silu:
+        y = F.silu(y)
+    if resample == 1:
+        y = F.avg_pool2d(y, 2, 2)
+    elif resample == 2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    return y
+
+
+@pytest.mark.parametrize("case", GN_CASES, ids=[str(c) for c in GN_CASES])
+def test_groupnorm_forward_backward(case):
+    B, H, W, Cc, silu, mod, rs = case
+    g = torch.Generator().manual_seed(11 + Cc + H)
+    x = (torch.randn(B, Cc, H, W, generator=g) * 1.7 + 0.6).requires_grad_(True)
+    gamma = 1 + 0.2 * torch.randn(Cc, generator=g)
+    beta = 0.2 * torch.randn(Cc, generator=g)
+    ss = 0.3 * torch.randn(B, 2 * Cc + 8, generator=g) if mod else None
+    ref = _gn_ref(x, gamma, beta, ss, silu, rs)
+    ld = Cc + 32  # strided input view
+    xbuf = torch.randn(B, H, W, ld, generator=g).to(DEV); xbuf[..., :Cc] = nhwc(x.detach())
+    stats = torch.zeros(B, 32, 2, device=DEV)
+    Ho, Wo = ref.shape[2:]
+    y = torch.empty(B, Ho, Wo, Cc, device=DEV)
+    gd, bd = gamma.to(DEV), beta.to(DEV)
+    ssd = ss.to(DEV).contiguous() if mod else None
+    L_.check(lib().osm_dbg_gn_forward(L_.ptr(xbuf), ld, L_.ptr(gd), L_.ptr(bd), L_.ptr(ssd), 2 * Cc + 8, silu, rs,
+                                      L_.ptr(stats), L_.ptr(y), B, H, W, Cc, L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(y), ref.detach()) < FP32_TOL
+    # backward with an addend in each mode and accumulation into a strided gradient view
+    dy = torch.randn(B, Cc, Ho, Wo, generator=g)
+    gref = torch.autograd.grad(ref, x, dy)[0]
+    dyd = nhwc(dy)
+    for add_mode in (0, 1, 2, 3):
+        if add_mode == 1:
+            add = torch.randn(B, Cc, H, W, generator=g); add_eff = add
+        elif add_mode == 2:
+            add = torch.randn(B, Cc, H // 2, W // 2, generator=g)
+            add_eff = 0.25 * F.interpolate(add, scale_factor=2, mode="nearest")
+        elif add_mode == 3:
+            add = torch.randn(B, Cc, 2 * H, 2 * W, generator=g); add_eff = 4 * F.avg_pool2d(add, 2, 2)
+        else:
+            add, add_eff = None, 0.0
+        addd = nhwc(add) if add is not None else None
+        prev = torch.randn(B, Cc, H, W, generator=g)
+        for acc in (0, 1):
+            dxbuf = torch.zeros(B, H, W, ld, device=DEV); dxbuf[..., :Cc] = nhwc(prev)
+            L_.check(lib().osm_dbg_gn_backward(L_.ptr(xbuf), ld, L_.ptr(gd), L_.ptr(bd), L_.ptr(ssd), 2 * Cc + 8, silu, rs,
+                                               L_.ptr(stats), L_.ptr(dyd), L_.ptr(addd), Cc, add_mode, L_.ptr(dxbuf), ld, acc,
+                                               B, H, W, Cc, L_.stream()))
+            torch.cuda.synchronize()
+            want = gref + add_eff + (prev if acc else 0.0)
+            assert rel_err(nchw(dxbuf)[:, :Cc], want) < 5e-5
+            assert float(dxbuf[..., Cc:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,L,Cc,heads", [(2, 64, 256, 4), (1, 256, 512, 8), (2, 1024, 128, 2), (3, 16, 1024, 16)])
+def test_attention_forward_backward(B, L, Cc, heads):
+    g = torch.Generator().manual_seed(L + Cc)
+    qkv = torch.randn(B, 3 * Cc, L, generator=g).requires_grad_(True)
+    ref = orc.qkv_attention_legacy(qkv, heads)  # [B, C, L]
+    go = torch.randn(B, Cc, L, generator=g)
+    gref = torch.autograd.grad(ref, qkv, go)[0]
+    qd = qkv.detach().permute(0, 2, 1).contiguous().to(DEV)  # [B, L, 3C]
+    out = torch.empty(B, L, Cc, device=DEV)
+    P = torch.empty(B * heads * L * L, device=DEV); D = torch.empty_like(P)
+    L_.check(lib().osm_dbg_attention(L_.ptr(qd), L_.ptr(out), L_.ptr(P), B, L, Cc, heads, L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(out.permute(0, 2, 1).cpu(), ref.detach()) < FP32_TOL
+    gq = torch.empty(B, L, 3 * Cc, device=DEV)
+    god = go.permute(0, 2, 1).contiguous().to(DEV)
+    L_.check(lib().osm_dbg_attention_bwd(L_.ptr(qd), L_.ptr(god), L_.ptr(gq), L_.ptr(P), L_.ptr(D), B, L, Cc, heads, L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(gq.permute(0, 2, 1).cpu(), gref) < 5e-5
