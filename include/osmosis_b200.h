@@ -78,6 +78,13 @@ int osm_unet_vjp_input(osm_unet_t h, const float* grad_out, float* grad_x, void*
 int osm_unet_launch_count(osm_unet_t h, int which /*0 fwd, 1 vjp*/);
 /* Algorithmic FLOPs (2*MAC) of one forward for the bound shape (convs + attention + linear).         */
 double osm_unet_forward_flops(osm_unet_t h);
+/* Measurement hook: runs program `which` (0 forward ops, 1 input-VJP ops; on the buffers of the last
+ * forward) with a CUDA-event pair around every op on `stream`, synchronises, and returns the number of
+ * ops n (<= cap) with per-op device time ms[n], kind[n] (0 conv, 1 gn_stats, 2 gn_apply, 3 gn_bwd,
+ * 4 attention fwd, 5 attention bwd, 6 linear), algorithmic flops[n] / HBM bytes[n], dims6[6n]
+ * (conv: H,W,Cin,Cout,taps,is_dgrad; norm: H,W,C; attention: L,C,heads).  Host arrays.                */
+int osm_unet_profile_ops(osm_unet_t h, int which, void* stream, int cap, float* ms, int* kinds, double* flops,
+                         double* bytes, int* dims6);
 
 /* ------------------------------------------------------------- sampler elementwise ---------------------
  * coef: [T][8] fp32 rows = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,

@@ -234,6 +234,18 @@ class UNetModel:
     def forward_flops(self):
         return float(self._L.osm_unet_forward_flops(self._h))
 
+    def profile_ops(self, which):
+        """Per-op device times of the forward (0) / input-VJP (1) program: list of dicts (kind, ms, flops, bytes, dims)."""
+        cap = 4096
+        ms, kinds = (C.c_float * cap)(), (C.c_int * cap)()
+        fl, by, dims = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int * (6 * cap))()
+        n = self._L.osm_unet_profile_ops(self._h, which, _lib.stream(), cap, ms, kinds, fl, by, dims)
+        if n < 0:
+            _lib.check(n)
+        names = ["conv", "gn_stats", "gn_apply", "gn_bwd", "attn_fwd", "attn_bwd", "linear"]
+        return [dict(kind=names[kinds[i]], ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i]),
+                     dims=[int(dims[6 * i + k]) for k in range(6)]) for i in range(n)]
+
     def _forward_raw(self, x, t, out=None):
         B, Cin, H, W = x.shape
         assert Cin == self.in_channels

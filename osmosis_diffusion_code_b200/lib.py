@@ -48,6 +48,8 @@ SIGNATURES = {
     "osm_unet_vjp_input": (_I, [_P, _P, _P, _P]),
     "osm_unet_launch_count": (_I, [_P, _I]),
     "osm_unet_forward_flops": (C.c_double, [_P]),
+    "osm_unet_profile_ops": (_I, [_P, _I, _P, _I, C.POINTER(_F), C.POINTER(_I), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(_I)]),
     "osm_posterior_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "osm_posterior_vjp": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "osm_sampler_update": (_I, [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
