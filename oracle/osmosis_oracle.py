@@ -496,3 +496,40 @@ def sample_loop(sd, cfg, tab, op, g, x_T, y, phis, noise_fn, steps=None):
 def ddpm_uncond_update(x, eps, z, alpha_t, alphabar_t, beta_tilde):
     """osmosis_utils/diffusion.py:122 (unguided ancestral update, fixed-small variance)."""
     return (1 / np.sqrt(alpha_t)) * (x - ((1 - alpha_t) / np.sqrt(1 - alphabar_t)) * eps) + np.sqrt(beta_tilde) * z
+
+
+# --------------------------------------------------------------------------------------
+# YAML -> oracle specs (measurements.py:108-136, 212-249, 333-361; condition_methods.py:63-107)
+# --------------------------------------------------------------------------------------
+
+
+def _floats(s):
+    if isinstance(s, (int, float)):
+        return (float(s),)
+    return tuple(float(v) for v in str(s).split(","))
+
+
+def specs_from_config(cfg, B=1):
+    """(Tables, OperatorSpec, GuidanceSpec, initial phis, phi names) from a parsed upstream YAML (dict of its top-level keys).
+
+    String-typed YAML values are parsed like the reference does."""
+    d = cfg["diffusion"]
+    tab = make_tables(d["steps"], d["noise_schedule"], d.get("timestep_respacing", ""))
+    o = cfg["measurement"]["operator"]
+    kind = o["name"]
+    val = _floats(o["value"])
+    if kind == "underwater_physical_revised":
+        names = ["phi_a", "phi_b", "phi_inf"]
+    else:
+        names = ["phi_ab", "phi_inf"]
+    eta = tuple(float(o.get(n + "_eta", 1e-5)) if o.get(n + "_learn_flag", True) else 0.0 for n in names)
+    phis = [torch.tensor(_floats(o[n]), dtype=torch.float32).repeat(B, 1)[..., None, None] for n in names]
+    op = OperatorSpec(kind, o.get("depth_type"), val if len(val) > 1 else val[0], eta)
+    p, sp = cfg["conditioning"]["params"], cfg["sample_pattern"]
+    clip = p.get("gradient_clip", "False").split(",")
+    g = GuidanceSpec(scale=_floats(p["scale"]), clip=float(clip[1]) if clip[0].strip().lower() == "true" else None,
+                         loss_weight=p.get("loss_weight"), weight_fn=p.get("weight_function"),
+                         aux=(cfg.get("aux_loss") or {}).get("aux_loss"), n_iter=sp["n_iter"],
+                         update_start=sp["update_start"], update_end=sp["update_end"],
+                         start_guidance=sp["start_guidance"], stop_guidance=sp["stop_guidance"], pattern=sp["pattern"])
+    return tab, op, g, phis, names
