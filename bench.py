@@ -103,13 +103,9 @@ def run_native(args):
     T = sampler.num_timesteps
     torch.manual_seed(a.manual_seed)
     img = torch.randn(B, 4, args.size, args.size, device=dev)
-    st = sampler.fused_state(model, cond, img, y)
-
-    def step(idx):
-        st["t_idx"].fill_(idx); st["t_model"].fill_(sampler._model_timestep(idx))
-        st["freeze"].fill_(int(is_freeze_phi(a.sample_pattern, idx, T)))
-        torch.randn_like(st["y"])                       # the reference's dead q_sample draw
-        sampler.fused_step(model, cond, st, img, torch.randn_like(img))
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    stepper = FusedStepper(sampler, model, cond, img, y, a.sample_pattern, cuda_graph=not args.no_cuda_graph)
+    step = stepper.step
 
     def barrier():
         if world > 1:
@@ -152,7 +148,8 @@ def run_native(args):
     _img, _vd, _loss, x0_cpu = samp2.p_sample_loop(model=model, x_start=x_start, measurement=y_host,
                                                    measurement_cond_fn=cond2.conditioning, record=False, save_root=None,
                                                    pretrain_model="osmosis", rgb_guidance=False, sample_pattern=a.sample_pattern,
-                                                   progress=lambda idx, loss: host_loss.append(loss))
+                                                   progress=lambda idx, loss: host_loss.append(loss),
+                                                   cuda_graph=not args.no_cuda_graph)
     f1.record()
     torch.cuda.synchronize()
     e2e_s = max(time.perf_counter() - t0, f0.elapsed_time(f1) / 1e3)  # device events and host clock agree; keep the larger
@@ -293,6 +290,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--config", default=os.path.join(ROOT, "configs", "osmosis_sample_config.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

@@ -194,17 +194,22 @@ def test_unet_forward_and_input_vjp_vs_reference_golden(conv_mode, tol):
     assert rel_err(gx.cpu(), gold["unet_gx"]) < tol
 
 
-def test_unet_batch_shard_invariance():
-    """B images at once == the same images one by one, bit for bit (no cross-image reduction anywhere)."""
+def test_unet_determinism_and_batch_shard_invariance():
+    """Same batch size twice -> bit-identical (fixed-order reductions, no float atomics).  B images at once vs one by one:
+    identical up to summation order (and the TF32 operand roundings it can flip) - the conv tile / split-K policy depends on the per-GPU batch (with equal
+    per-GPU batches, as in the weak-scaling runs, every image sees the same policy on every rank)."""
     m = model("tc")
     x, t, cot = case_inputs("unet")
     xd, td, cd = x.to(DEV), t.to(DEV), cot.to(DEV)
     full = m._forward_raw(xd, td.float()).clone()
     gfull = m._vjp_raw(cd).clone()
+    full2 = m._forward_raw(xd, td.float()).clone()
+    gfull2 = m._vjp_raw(cd).clone()
+    assert torch.equal(full, full2) and torch.equal(gfull, gfull2)
     for b in range(x.shape[0]):
         one = m._forward_raw(xd[b:b + 1], td[b:b + 1].float())
         gone = m._vjp_raw(cd[b:b + 1].contiguous())
-        assert torch.equal(one[0], full[b]) and torch.equal(gone[0], gfull[b])
+        assert rel_err(one[0].cpu(), full[b].cpu()) < 1e-4 and rel_err(gone[0].cpu(), gfull[b].cpu()) < 1e-4
 
 
 # ------------------------------------------------------------------------------------------- steps and loop

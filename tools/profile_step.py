@@ -55,17 +55,18 @@ def main():
     ap.add_argument("--config", default="configs/osmosis_sample_config.yaml")
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     B = args.batch
     a, model, op, cond, sampler, y = build(args.config, B, args.size)
     torch.manual_seed(a.manual_seed)
     img = torch.randn(B, 4, args.size, args.size, device="cuda")
-    st = sampler.fused_state(model, cond, img, y)
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    stepper = FusedStepper(sampler, model, cond, img, y, a.sample_pattern, cuda_graph=not args.no_graph)
     T = sampler.num_timesteps
 
     def step(idx, freeze):
-        st["t_idx"].fill_(idx); st["t_model"].fill_(sampler._model_timestep(idx)); st["freeze"].fill_(int(freeze))
-        sampler.fused_step(model, cond, st, img, torch.randn_like(img))
+        stepper.step(idx, freeze=freeze)
 
     for k in range(3):
         step(T - 1 - k, True)
