@@ -209,8 +209,10 @@ int operator_fwd_launch(int op_kind, int depth_kind, const float* dv, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused guidance / phi-optimisation loop.  One CTA per image (512 threads); the image's 7 planes
-// (x0 RGBD + y RGB, 1.8 MB at 256x256) stay L2-resident across the n_iter passes.
+// Fused guidance / phi-optimisation loop.  One thread-block CLUSTER of GUID_CLUSTER CTAs per image (512 threads each, a
+// pixel slice per CTA); the image's 7 planes (x0 RGBD + y RGB, 1.8 MB at 256x256) stay L2-resident across the n_iter
+// passes.  The 10 per-evaluation sums are block-reduced, exchanged through distributed shared memory and added in rank
+// order by every CTA, so all CTAs of an image take identical phi steps (deterministic, no atomics, no host round trip).
 //
 // Per evaluation:
 //   r_c = (y_c - (2 uw_c - 1)) w ;  L = ||r||_2 ;  dL/dphi = (1/L) sum_pix r_c * d r_c/d phi
@@ -219,6 +221,20 @@ int operator_fwd_launch(int op_kind, int depth_kind, const float* dv, const floa
 // ------------------------------------------------------------------------------------------------
 constexpr int GUID_THREADS = 512;
 constexpr int GUID_NRED = 10;
+constexpr int GUID_CLUSTER = 8;
+
+__device__ __forceinline__ void guid_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double guid_ld_dsmem_f64(const double* local, uint32_t cta) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -250,13 +266,36 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* red /*[32*NV 
   __syncthreads();
 }
 
+// Sum of the block totals over the CTAs of the cluster (rank order).  `slot` is this CTA's exchange buffer [2][NV]; the
+// parity alternates per call so one cluster barrier per call suffices.
+template <int NV>
+__device__ __forceinline__ void cluster_sum(double (&v)[NV], double* slot, double* tot, int& parity, int csize) {
+  if (csize == 1) return;
+  if (threadIdx.x < NV) slot[parity * NV + threadIdx.x] = v[threadIdx.x];
+  guid_cluster_sync();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int q = 0; q < csize; ++q) t += guid_ld_dsmem_f64(&slot[parity * NV + threadIdx.x], (uint32_t)q);
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = tot[k];
+  __syncthreads();
+  parity ^= 1;
+}
+
 __global__ void __launch_bounds__(GUID_THREADS, 1)
 guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, const float* __restrict__ y,
                          float* __restrict__ phi_io, const int32_t* __restrict__ freeze_flag, float* __restrict__ g_x0,
-                         float* __restrict__ losses, int HW) {
+                         float* __restrict__ losses, int HW, int csize) {
   __shared__ double red[32 * GUID_NRED + GUID_NRED];
+  __shared__ double xslot[2 * GUID_NRED], xtot[GUID_NRED];
   __shared__ float sphi[9];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / csize, rank = blockIdx.x % csize;
+  int parity = 0;
+  const int per = (HW + csize - 1) / csize;
+  const int i0 = rank * per, i1 = min(HW, i0 + per);
   const float* xb = x0 + (size_t)b * 4 * HW;
   const float* yb = y + (size_t)b * 3 * HW;
   float* gb = g_x0 + (size_t)b * 4 * HW;
@@ -268,7 +307,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
 
   // phi-independent reductions: channel means (avrg_loss) and the val_loss sum
   double pre[4] = {0, 0, 0, 0};
-  for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+  for (int i = i0 + threadIdx.x; i < i1; i += GUID_THREADS) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float v = xb[c * (size_t)HW + i];
@@ -278,6 +317,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
     }
   }
   block_sum<4>(pre, red);
+  cluster_sum<4>(pre, xslot, xtot, parity, csize);
   float mean_c[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) mean_c[c] = (float)(pre[c] / HW);
@@ -291,7 +331,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
     double acc[GUID_NRED];
 #pragma unroll
     for (int k = 0; k < GUID_NRED; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+    for (int i = i0 + threadIdx.x; i < i1; i += GUID_THREADS) {
       const float xd = xb[3 * (size_t)HW + i];
       const float d = depth_convert(df, xd);
       const float w = P.weight_kind ? depth_convert(wf, xd) : 1.0f;
@@ -312,6 +352,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
       }
     }
     block_sum<GUID_NRED>(acc, red);
+    cluster_sum<GUID_NRED>(acc, xslot, xtot, parity, csize);
     Lnorm = (float)sqrt(acc[0]);
     const float invL = 1.0f / Lnorm;
 
@@ -319,7 +360,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
       // d total / d x0 at the current phi (before this evaluation's SGD step)
       const float ka = P.gamma_avrg / (float)HW;
       const float kv = P.gamma_val * 2.0f / (3.0f * (float)HW);
-      for (int i = threadIdx.x; i < HW; i += GUID_THREADS) {
+      for (int i = i0 + threadIdx.x; i < i1; i += GUID_THREADS) {
         const float xd = xb[3 * (size_t)HW + i];
         const float d = depth_convert(df, xd);
         const float w = P.weight_kind ? depth_convert(wf, xd) : 1.0f;
@@ -370,6 +411,8 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
       __syncthreads();
     }
   }
+  if (csize > 1) guid_cluster_sync();  // no CTA may exit while a peer can still read its exchange slots
+  if (rank != 0) return;
   if (threadIdx.x < 9) phi_io[9 * b + threadIdx.x] = sphi[threadIdx.x];
   if (threadIdx.x == 0) {
     losses[4 * b + 0] = Lnorm;
@@ -383,8 +426,18 @@ int guidance_phi_loop_launch(const osm_guidance_params* p, const float* x0, cons
                              const int32_t* freeze_flag, float* g_x0, float* losses, int B, int HW, cudaStream_t s) {
   if (p->op_kind < 0 || p->op_kind > 2) return fail(OSM_ERR_INVALID, "guidance: unknown operator kind");
   if (p->n_iter < 1) return fail(OSM_ERR_INVALID, "guidance: n_iter must be >= 1");
-  guidance_phi_loop_kernel<<<B, GUID_THREADS, 0, s>>>(*p, x0, y, phi, freeze_flag, g_x0, losses, HW);
-  OSM_LAUNCH_CHECK("guidance_phi_loop_kernel");
+  const int csize = (HW >= GUID_CLUSTER * GUID_THREADS) ? GUID_CLUSTER : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(B * csize));
+  cfg.blockDim = dim3(GUID_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OSM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, guidance_phi_loop_kernel, *p, x0, y, phi, freeze_flag, g_x0, losses, HW, csize));
   return OSM_OK;
 }
 
