@@ -28,7 +28,9 @@ def build(cfg_path, B, size, conv_mode="tc", dev="cuda"):
     a = arguments_from_file(cfg_path)
     um = dict(a.unet_model); um["model_path"] = ""
     t0 = time.time()
-    model = create_model(**um, conv_mode=conv_mode)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # create_model reports the missing checkpoint on stdout, like the reference
+        model = create_model(**um, conv_mode=conv_mode)
     sd = synth_state_dict(model.param_specs(), um["num_channels"], seed=7, delta=0.05)
     model.load_state_dict(sd); del sd
     model.to(dev)
