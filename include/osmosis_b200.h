@@ -164,6 +164,11 @@ int osm_dbg_gn_backward(const float* x, int ldx, const float* gamma, const float
 int osm_dbg_attention(const float* qkv, float* out, float* scratch_P, int B, int L, int C, int heads, void* stream);
 int osm_dbg_attention_bwd(const float* qkv, const float* g_out, float* g_qkv, float* scratch_P, float* scratch_D, int B,
                           int L, int C, int heads, void* stream);
+/* Fused tcgen05 flash attention (product mode).  qkvT [B,3C,L], lse/Dv [B,heads,L], g_outT [B,C,L] are caller scratch; the
+ * backward expects qkvT/out/lse as left by the forward on the same qkv. */
+int osm_dbg_attention_flash(const float* qkv, float* qkvT, float* out, float* lse, int B, int L, int C, int heads, void* stream);
+int osm_dbg_attention_flash_bwd(const float* qkv, float* qkvT, float* out, float* lse, float* Dv, const float* g_out,
+                                float* g_outT, float* g_qkv, int B, int L, int C, int heads, void* stream);
 
 #ifdef __cplusplus
 }

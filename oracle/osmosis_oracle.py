@@ -432,6 +432,9 @@ class GuidanceSpec:
     start_guidance: float = 1.0
     stop_guidance: float = 0.0
     pattern: str = "pcgs"
+    s_start: float = 0.1
+    s_end: float = 0.0
+    local_M: int = 1
 
 
 def is_freeze_phi(g: GuidanceSpec, idx: int, T: int) -> bool:
@@ -481,16 +484,51 @@ def guided_step(sd, cfg: UNetConfig, tab: Tables, op: OperatorSpec, g: GuidanceS
                 log_variance=logvar.detach(), model_out=out.detach())
 
 
+def guidance_on(g: GuidanceSpec, idx: int, T: int) -> bool:
+    """guidance_flag of gaussian_diffusion.py:218-222."""
+    return g.pattern == "original" or g.pattern is None or (g.start_guidance * T >= idx >= g.stop_guidance * T)
+
+
+def alternate_length(g: GuidanceSpec, idx: int, T: int) -> int:
+    """utils.py:593-630 (set_alternate_length): local_M inside all three windows, else 1."""
+    if g.pattern is None or g.pattern == "original":
+        return 1
+    for lo, hi in ((g.stop_guidance, g.start_guidance), (g.update_end, g.update_start), (g.s_end, g.s_start)):
+        if idx > hi * T or idx < lo * T:
+            return 1
+    return g.local_M
+
+
+def unguided_step(sd, cfg: UNetConfig, tab: Tables, x: torch.Tensor, idx: int, noise: torch.Tensor):
+    """A loop iteration with guidance_flag False (gaussian_diffusion.py:262-271): img = mean (+ sigma z unless t == 0)."""
+    B = x.shape[0]
+    with torch.no_grad():
+        t_model = torch.full((B,), tab.timestep_map[idx], dtype=torch.int64)
+        out = unet_forward(sd, cfg, x, t_model)
+        x0, mean, logvar = posterior(tab, idx, x, out)
+        x_next = mean.clone()
+        if idx != 0:
+            x_next = x_next + torch.exp(0.5 * logvar) * noise
+    return dict(x_next=x_next, pred_xstart=x0, mean=mean, log_variance=logvar)
+
+
 def sample_loop(sd, cfg, tab, op, g, x_T, y, phis, noise_fn, steps=None):
-    """p_sample_loop (gaussian_diffusion.py:179-340).  noise_fn(idx) -> [B,4,H,W] (RNG order: Appendix C)."""
-    x, last = x_T, None
-    idxs = list(range(tab.num_timesteps))[::-1]
+    """p_sample_loop (gaussian_diffusion.py:179-340).  noise_fn(idx) -> [B,4,H,W] (RNG order: Appendix C); with an
+    alternate length M > 1 it is called M times per index (one draw per repetition, :266)."""
+    x, last, loss = x_T, None, None
+    T = tab.num_timesteps
+    idxs = list(range(T))[::-1]
     if steps is not None:
         idxs = idxs[:steps]
     for idx in idxs:
-        last = guided_step(sd, cfg, tab, op, g, x, y, phis, idx, noise_fn(idx))
-        x, phis = last["x_next"], last["phis"]
-    return x, phis, last["loss"], last["pred_xstart"]
+        for _ in range(alternate_length(g, idx, T)):
+            if guidance_on(g, idx, T):
+                last = guided_step(sd, cfg, tab, op, g, x, y, phis, idx, noise_fn(idx))
+                phis, loss = last["phis"], last["loss"]
+            else:
+                last = unguided_step(sd, cfg, tab, x, idx, noise_fn(idx))
+            x = last["x_next"]
+    return x, phis, loss, last["pred_xstart"]
 
 
 def ddpm_uncond_update(x, eps, z, alpha_t, alphabar_t, beta_tilde):
@@ -531,5 +569,6 @@ def specs_from_config(cfg, B=1):
                          loss_weight=p.get("loss_weight"), weight_fn=p.get("weight_function"),
                          aux=(cfg.get("aux_loss") or {}).get("aux_loss"), n_iter=sp["n_iter"],
                          update_start=sp["update_start"], update_end=sp["update_end"],
-                         start_guidance=sp["start_guidance"], stop_guidance=sp["stop_guidance"], pattern=sp["pattern"])
+                         start_guidance=sp["start_guidance"], stop_guidance=sp["stop_guidance"], pattern=sp["pattern"],
+                         s_start=sp.get("s_start", 1), s_end=sp.get("s_end", 0), local_M=sp.get("local_M", 1))
     return tab, op, g, phis, names

@@ -309,3 +309,46 @@ def test_loop_teacher_forced_chain_vs_oracle():
     assert float(d.max()) < 0.2
     for n, p in zip(names, pho):
         assert maxdiff(getattr(op, n).cpu(), p) < 1e-4
+
+
+def test_loop_guidance_window_and_alternate_length_vs_oracle():
+    """sample_pattern with a guidance window (unguided steps at both ends, gaussian_diffusion.py:218-222, :262-264) and an
+    alternate length local_M = 2 inside [s_end, s_start] (utils.py:593-630): the fused loop (FusedStepper, with and without
+    CUDA-graph replay) against the oracle's loop with the same injected noise, exact mode."""
+    cname = "osmosis"
+    cfg, op, cond, sampler = _native_objects(cname, 1)
+    sp = cfg["sample_pattern"]
+    sp.update(start_guidance=0.8, stop_guidance=0.2, update_start=0.7, update_end=0.2, s_start=0.5, s_end=0.3, local_M=2)
+    T = sampler.num_timesteps
+    tab, ospec, gspec, phis, names = oracle_specs_from_cfg(cfg, 1)
+    assert [orc.alternate_length(gspec, i, T) for i in range(T)].count(2) >= 1
+    assert not orc.guidance_on(gspec, T - 1, T) and not orc.guidance_on(gspec, 0, T)
+    y, _ = case_inputs("meas:" + cname)
+    g = torch.Generator().manual_seed(5)
+    x_T = torch.randn(1, 4, *y.shape[2:], generator=g)
+    draws = [torch.randn(1, 4, *y.shape[2:], generator=g) for _ in range(3 * T)]
+    it = iter(draws)
+    xo, pho, losso, x0o = orc.sample_loop(small_state_dict(), small_cfg(), tab, ospec, gspec, x_T, y, phis, lambda i: next(it))
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import set_alternate_length
+    m = model("fp32")
+    for use_graph in (False, True):
+        cfg, op, cond, sampler = _native_objects(cname, 1)
+        cfg["sample_pattern"].update(sp)
+        img = x_T.to(DEV).clone()
+        stepper = FusedStepper(sampler, m, cond, img, y.to(DEV), cfg["sample_pattern"], cuda_graph=use_graph)
+        k = 0
+        n_steps = 0
+        for idx in range(T)[::-1]:
+            for _ in range(set_alternate_length(cfg["sample_pattern"], idx, T)):
+                stepper._draw_into = lambda buf, _k=k: buf.copy_(draws[_k].to(DEV)) if buf.shape[1] == 4 else buf.zero_()
+                stepper.step(idx)
+                k += 1
+                n_steps += 1
+        torch.cuda.synchronize()
+        assert n_steps == T + [orc.alternate_length(gspec, i, T) for i in range(T)].count(2)
+        d = (img.cpu() - xo).abs()
+        assert float((d < 1e-3).float().mean()) > 0.995, use_graph
+        assert float(d.max()) < 0.2
+        for n, p in zip(names, pho):
+            assert maxdiff(getattr(op, n).cpu(), p) < 1e-4
