@@ -67,6 +67,8 @@ CONV_CASES = [
     (2, 32, 32, 256, 256, 9),
     (1, 32, 32, 512, 1536, 1),
     (1, 64, 64, 512, 512, 9),
+    # enough 256-pixel tiles for the policy to pick the 256x256-tile persistent kernel (conv_tc_persist_m256_kernel)
+    (1, 256, 128, 128, 256, 9),
 ]
 
 
@@ -226,3 +228,60 @@ def test_attention_forward_backward(B, L, Cc, heads):
     L_.check(lib().osm_dbg_attention_bwd(L_.ptr(qd), L_.ptr(god), L_.ptr(gq), L_.ptr(P), L_.ptr(D), B, L, Cc, heads, L_.stream()))
     torch.cuda.synchronize()
     assert rel_err(gq.permute(0, 2, 1).cpu(), gref) < 5e-5
+
+
+@pytest.mark.parametrize("cout,silu,mod", [(256, 1, True), (512, 0, False), (128, 1, False)])
+def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
+    """GroupNorm statistics reduced in the tcgen05 conv's epilogue (conv_epilogue.cuh) + the finalize kernel, checked
+    against torch statistics of the conv's OWN output (so the TF32 rounding of the conv itself does not enter):
+    mode 1 = forward mean / rstd (nn.py:17-19); mode 2 = the two means of the GroupNorm input gradient."""
+    B, H, W, cin, taps = 2, 128, 128, 64, 9     # 256 full 128-pixel tiles -> the persistent kernel
+    g = torch.Generator().manual_seed(3 + cout)
+    x = torch.randn(B, H, W, cin, generator=g).to(DEV)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * taps)
+    bias = (torch.randn(cout, generator=g) + 0.5).to(DEV)
+    wf, _, cout_p, cin_p = pack_weight(w, taps, round_tf32=True)
+    out = torch.empty(B, H, W, cout, device=DEV)
+    part = torch.full((B * 256 * 4 * 64,), float("nan"), device=DEV)
+    coef = torch.empty(B * cout * 4, device=DEV)
+    stats = torch.zeros(B, 32, 2, device=DEV)
+    fused = C.c_int(0)
+
+    def call(mode, gx=None, gamma=None, beta=None, ss=None, fstats=None, dst=None):
+        L_.check(lib().osm_dbg_conv_stats(L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(out), cout, B, H, W, cin, cout, taps, mode,
+                                          L_.ptr(gx), cout, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * cout, silu, L_.ptr(fstats),
+                                          L_.ptr(part), L_.ptr(coef), L_.ptr(dst), C.addressof(fused), L_.stream()))
+        torch.cuda.synchronize()
+
+    call(1, dst=stats)
+    assert fused.value == 1, "policy did not pick the persistent kernel for this shape"
+    cpg = cout // 32
+    o = out.double().view(B, H * W, 32, cpg)
+    mean = o.mean(dim=(1, 3)); var = o.var(dim=(1, 3), unbiased=False)
+    assert float((stats[:, :, 0].double() - mean).abs().max()) < 1e-5 * float(o.abs().max())
+    assert float((stats[:, :, 1].double() * torch.sqrt(var + 1e-5) - 1).abs().max()) < 1e-5
+    # mode 2: out plays dL/d(activation) of a GroupNorm with input gx
+    gx = (torch.randn(B, H, W, cout, generator=g) * 1.5 + 0.7).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(cout, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(cout, generator=g)).to(DEV)
+    ss = (0.3 * torch.randn(B, 2 * cout, generator=g)).to(DEV) if mod else None
+    xg = gx.double().view(B, H * W, 32, cpg)
+    m = xg.mean(dim=(1, 3), keepdim=True); v = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    rstd = 1.0 / torch.sqrt(v + 1e-5)
+    fstats = torch.stack([m.squeeze(), rstd.squeeze()], dim=-1).float().contiguous()
+    bst = torch.zeros(B, 32, 2, device=DEV)
+    call(2, gx=gx, gamma=gamma, beta=beta, ss=ss, fstats=fstats, dst=bst)
+    xh = (xg - m) * rstd
+    ga, be = gamma.double().view(1, 1, 32, cpg), beta.double().view(1, 1, 32, cpg)
+    sc1 = 1 + ss[:, :cout].double().view(B, 1, 32, cpg) if mod else 1.0
+    sh = ss[:, cout:].double().view(B, 1, 32, cpg) if mod else 0.0
+    pre = (xh * ga + be) * sc1 + sh
+    dy = out.double().view(B, H * W, 32, cpg)
+    if silu:
+        sg = torch.sigmoid(pre)
+        dy = dy * sg * (1 + pre * (1 - sg))
+    d = dy * sc1 * ga
+    m1 = d.mean(dim=(1, 3)); m2 = (d * xh).mean(dim=(1, 3))
+    scale = float(d.abs().mean())
+    assert float((bst[:, :, 0].double() - m1).abs().max()) < 2e-4 * scale
+    assert float((bst[:, :, 1].double() - m2).abs().max()) < 2e-4 * scale

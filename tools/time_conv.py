@@ -24,6 +24,7 @@ def main():
         v = [int(t) for t in sh.split(",")]
         B, H, W, cin, cout, taps = v[:6]
         res_mode = v[6] if len(v) > 6 else 0
+        stat_mode = v[7] if len(v) > 7 else 0   # 1 / 2: GroupNorm statistics reduced in the epilogue (+ finalize kernel)
         k = 3 if taps == 9 else 1
         g = torch.Generator().manual_seed(1)
         w = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * taps)).to(dev)
@@ -34,12 +35,23 @@ def main():
         res = torch.randn(B, H, W, cout, device=dev) if res_mode else None
         out = torch.empty(B, H, W, cout, device=dev)
         ts = []
+        if stat_mode:
+            import ctypes
+            gx = torch.randn(B, H, W, cout, device=dev); gam = torch.ones(cout, device=dev); bet = torch.zeros(cout, device=dev)
+            fst = torch.zeros(B, 32, 2, device=dev); fst[..., 1] = 1.0
+            part = torch.empty(B * (H * W // 128 + 64) * 256, device=dev); coef = torch.empty(B * cout * 4, device=dev)
+            so = torch.zeros(B, 32, 2, device=dev); fused = ctypes.c_int(0)
         for rep in range(12):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            L_.check(lib.osm_dbg_conv(0, L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(res), cout, res_mode, L_.ptr(out), cout, 0,
-                                      B, H, W, cin, cout, taps, L_.stream()))
+            if stat_mode:
+                L_.check(lib.osm_dbg_conv_stats(L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(out), cout, B, H, W, cin, cout, taps,
+                                                stat_mode, L_.ptr(gx), cout, L_.ptr(gam), L_.ptr(bet), None, 0, 1, L_.ptr(fst),
+                                                L_.ptr(part), L_.ptr(coef), L_.ptr(so), ctypes.addressof(fused), L_.stream()))
+            else:
+                L_.check(lib.osm_dbg_conv(0, L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(res), cout, res_mode, L_.ptr(out), cout, 0,
+                                          B, H, W, cin, cout, taps, L_.stream()))
             e1.record(); torch.cuda.synchronize()
             if rep >= 2:
                 ts.append(e0.elapsed_time(e1))
