@@ -147,6 +147,21 @@ int osm_operator_forward(int op_kind, int depth_kind, const float depth_val[3], 
 int osm_guidance_phi_loop(const osm_guidance_params* p, const float* x0, const float* y, float* phi,
                           const int32_t* freeze_flag, float* g_x0, float* losses, int B, int HW, void* stream);
 
+/* ------------------------------------------------------------ post-processing of finished samples --------
+ * Replaces the per-image CPU block after p_sample_loop in osmosis_sampling.py:207-292 (batched, on the device).
+ * x0 [B,4,HW] (pred_xstart), y [B,3,HW] in [-1,1] (the measurement), phi [B,9] as in osm_guidance_phi_loop.
+ *   rgb_clip   clamp(0.5 (x0_rgb + 1), 0, 1)                                   (:214-215)
+ *   degraded   2 A_phi(x0) - 1, norm_loss[b] = || degraded - y ||_2            (:245-251, :283-291)
+ *   recon      exp(phi_a d) (0.5 (y + 1) - backscatter)                        (:254-256, :286-287)          */
+int osm_postprocess(int op_kind, int depth_kind, const float depth_val[3], const float* x0, const float* y, const float* phi,
+                    float* rgb_clip, float* degraded, float* recon, float* norm_loss, int B, int HW, void* stream);
+/* min_max_norm_range (q_low = 0, q_high = 1) / min_max_norm_range_percentile of each of the B planes of n elements
+ * (osmosis_utils/utils.py:46-114): clip to torch.quantile(img, q) (linear interpolation), map [min, max] to [vmin, vmax]. */
+int osm_minmax_percentile(const float* img, float* out, int B, int n, float q_low, float q_high, float vmin, float vmax,
+                          void* stream);
+/* depth_tensor_to_color_image (utils.py:748-763): matplotlib-style lookup of img in [0,1] in a [256][3] table -> [B,3,n] */
+int osm_colormap(const float* img, const float* lut, float* out, int B, int n, void* stream);
+
 /* ------------------------------------------------------------ layer-level entry points -----------------
  * Used by the kernel parity tests (tests/test_kernels_gpu.py); NHWC fp32 with an explicit pixel stride
  * `ld` (elements).  Not part of the sampling API.                                                     */

@@ -415,6 +415,59 @@ def guidance_losses(spec: OperatorSpec, x0: torch.Tensor, y: torch.Tensor, phis:
 
 
 # --------------------------------------------------------------------------------------
+# post-processing of a finished sample  (osmosis_sampling.py:207-292, osmosis_utils/utils.py:46-114, 748-763)
+# --------------------------------------------------------------------------------------
+def min_max_norm_range(img: torch.Tensor, vmin=0.0, vmax=1.0) -> torch.Tensor:
+    """utils.py:46-76 for a 3-D tensor: global min / max -> [vmin, vmax]; zeros when constant."""
+    lo, hi = img.min(), img.max()
+    if lo == hi:
+        return torch.zeros_like(img)
+    scale = (float(vmax) - float(vmin)) / (hi - lo)
+    return (img - lo) * scale + float(vmin)
+
+
+def min_max_norm_range_percentile(img: torch.Tensor, vmin=0.0, vmax=1.0, percent_low=0.0, percent_high=1.0) -> torch.Tensor:
+    """utils.py:79-114 for a 3-D tensor: clip to torch.quantile(img, q) at both ends, then min-max normalise."""
+    q_lo = torch.quantile(img, q=percent_low)
+    q_hi = torch.quantile(img, q=percent_high)
+    clip = torch.clamp(img, q_lo, q_hi)
+    lo, hi = clip.min(), clip.max()
+    if lo == hi:
+        return torch.zeros_like(clip)
+    scale = (float(vmax) - float(vmin)) / (hi - lo)
+    return (clip - lo) * scale + float(vmin)
+
+
+def apply_colormap(img01: torch.Tensor, lut: np.ndarray) -> torch.Tensor:
+    """utils.py:748-763 with the colormap given as its [256,3] table: matplotlib's Colormap.__call__ maps a float x in
+    [0,1] to entry int(x * 256), with x == 1 sent to the last entry.  img01 [H,W] -> [3,H,W]."""
+    idx = np.clip((img01.numpy().astype(np.float32) * np.float32(256.0)).astype(np.int64), 0, 255)
+    return torch.tensor(np.asarray(lut, dtype=np.float32)[idx]).permute(2, 0, 1)
+
+
+def postprocess(spec: OperatorSpec, x0: torch.Tensor, y: torch.Tensor, phis: list) -> dict:
+    """The block after p_sample_loop in osmosis_sampling.py:207-292 for ONE image (x0 [1,4,H,W], y [1,3,H,W] in [-1,1],
+    phis as in operator_forward): clipped RGB, depth normalisations, re-degraded image + its norm, restored image."""
+    rgb = x0[0, 0:-1]
+    depth = x0[0, -1].unsqueeze(0)
+    rgb01 = 0.5 * (rgb + 1)
+    d = convert_depth(depth.repeat(3, 1, 1), spec.depth_type, spec.value)
+    if spec.kind == "underwater_physical_revised":
+        pa, pb, pinf = (p[0] for p in phis)
+    else:
+        pa = pb = phis[0][0]
+        pinf = phis[1][0]
+    ones = torch.ones_like(rgb)
+    back = (pinf * ones) * (1 - torch.exp(-(pb * ones) * d))
+    att = torch.exp(-(pa * ones) * d)
+    degraded = 2 * (rgb01 * att + back) - 1
+    ref01 = 0.5 * (y[0] + 1)
+    return dict(sample_rgb_01_clip=torch.clamp(rgb01, min=0, max=1), sample_depth_mm=min_max_norm_range(depth),
+                sample_depth_vis_pmm=min_max_norm_range_percentile(depth, 0, 1, 0.03, 0.99), degraded_image=degraded,
+                norm_loss=torch.linalg.norm(degraded - y[0]), sample_rgb_recon=torch.exp((pa * ones) * d) * (ref01 - back))
+
+
+# --------------------------------------------------------------------------------------
 # one guided step and the loop  (gaussian_diffusion.py:179-340, condition_methods.py:146-231)
 # --------------------------------------------------------------------------------------
 

@@ -174,8 +174,10 @@ class GaussianDiffusion:
         if steps is not None:
             idxs = idxs[:steps]
         if fused:
+            rec = dict(record_every=record_every, save_grids_path=kwargs.get("save_grids_path", None),
+                       original_file_name=kwargs.get("original_file_name", "image_0")) if record else None
             return self._loop_fused(model, cond, x_start, measurement, sample_pattern, idxs, noise_mode, kwargs.get("progress"),
-                                    kwargs.get("cuda_graph", True))
+                                    kwargs.get("cuda_graph", True), record=rec)
         return self._loop_autograd(model, measurement_cond_fn, x_start, measurement, sample_pattern, idxs)
 
     def _draw(self, like, noise_mode):
@@ -236,7 +238,8 @@ class GaussianDiffusion:
                                         _lib.ptr(st["zero_scale"]), -1.0, _lib.ptr(st["logvar"]), _lib.ptr(noise),
                                         _lib.ptr(st["t_idx"]), _lib.ptr(img), None, B, Cc, HW, s))
 
-    def _loop_fused(self, model, cond, x_start, measurement, sample_pattern, idxs, noise_mode, progress=None, cuda_graph=True):
+    def _loop_fused(self, model, cond, x_start, measurement, sample_pattern, idxs, noise_mode, progress=None, cuda_graph=True,
+                    record=None):
         """`measurement` may live in (pinned) host memory: it is then streamed to the device every step.  `progress(idx,
         loss[B] numpy)` is called after every step when given - it costs one device->host read per step, which is what
         the reference's progress bar does (gaussian_diffusion.py:276-296)."""
@@ -258,11 +261,39 @@ class GaussianDiffusion:
                 stepper.step(idx)
             if progress is not None:
                 progress(idx, st["losses"][:, 0].cpu().numpy())
+            # `record` (gaussian_diffusion.py:310-326): keep pred_xstart of image 0 every record_every steps.  The snapshot
+            # is a device-to-device copy on the stream (no host sync in the loop); images are built after the loop.
+            if record is not None and ((idx % record["record_every"] == 0) or (idx == 0) or (idx == 999)):
+                record.setdefault("frames", []).append(st["x0"][0:1].clone())
+        if record is not None:
+            self.last_record = self._finish_record(record)
         variable_dict = cond.operator.optimize(freeze_phi=True)
         loss = st["losses"][:, 0].cpu().numpy()
         self.last_gradients = st["grad"]
         self.last_aux = st["losses"]
         return img, variable_dict, loss, st["x0"].detach().cpu()
+
+    @staticmethod
+    def _finish_record(record):
+        """Builds the reference's process grid (gaussian_diffusion.py:310-333) from the recorded pred_xstart frames: clipped
+        RGB row over a percentile-normalised (0.05 / 0.99), colour-mapped depth row; saved as <name>_process.png when a
+        grid path is given.  Returns dict(rgb=[n,3,H,W], depth_color=[n,3,H,W]) on the device (+ 'grid' on the host)."""
+        frames = torch.cat(record.get("frames", []), 0) if record.get("frames") else None
+        if frames is None:
+            return None
+        rgb = torch.clamp(0.5 * (frames[:, 0:3] + 1), 0, 1)
+        depth_pmm = utilso.min_max_norm_range_percentile(frames[:, 3:4].contiguous(), percent_low=0.05, percent_high=0.99)
+        depth_color = utilso.depth_tensor_to_color_image(depth_pmm) if frames.shape[0] > 1 else \
+            utilso.depth_tensor_to_color_image(depth_pmm)[None]
+        out = dict(rgb=rgb, depth_color=depth_color)
+        if record.get("save_grids_path") is not None:
+            from torchvision.utils import make_grid
+            import torchvision.transforms.functional as tvtf
+            import os
+            grid = make_grid(list(rgb.cpu()) + list(depth_color.cpu()), nrow=rgb.shape[0])
+            tvtf.to_pil_image(grid).save(os.path.join(record["save_grids_path"], f"{record['original_file_name']}_process.png"))
+            out["grid"] = grid
+        return out
 
     def _loop_autograd(self, model, measurement_cond_fn, x_start, measurement, sample_pattern, idxs):
         img = x_start

@@ -42,3 +42,21 @@ def case_inputs(key: str):
     if kind in ("x", "noise"):
         return torch.randn(1, 4, SMALL_HW, SMALL_HW, generator=_gen(key))
     raise KeyError(key)
+
+
+# ---- post-processing helpers (tests/golden/make_golden_post.py) ----
+POST_CASES = {"smooth64": (64, 64, 11), "noise48x80": (48, 80, 12), "ties32": (32, 32, 13), "const16": (16, 16, 14)}
+
+
+def post_inputs(name: str) -> torch.Tensor:
+    """Seeded depth-like [1,H,W] fp32 planes: smooth, white noise, heavily quantised (many ties), constant."""
+    H, W, seed = POST_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    if name.startswith("smooth"):
+        d = torch.nn.functional.interpolate(torch.rand(1, 1, 8, 8, generator=g), size=(H, W), mode="bilinear", align_corners=False)[0]
+        return (2 * d - 1).contiguous()
+    if name.startswith("noise"):
+        return torch.randn(1, H, W, generator=g) * 1.7
+    if name.startswith("ties"):
+        return torch.round(torch.randn(1, H, W, generator=g) * 2) / 4
+    return torch.full((1, H, W), 0.25)
