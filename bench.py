@@ -223,6 +223,23 @@ def run_native(args):
                     tf32_peak_measured=tf32, frac_of_tf32_sustained=round(dom_tf / tf32["tf32_tflops_sustained"], 4),
                     flops_per_launch=dom[0]["flops"], launches_averaged=len(dom), ms_per_launch=round(dom_ms, 4),
                     all_convs_tflops=round(conv_all_tf, 1), groupnorm_kernels_gbs=round(norm_gbs, 0), hbm_peak_gbs=peaks["hbm"])
+    # secondary rooflines (informational): the HBM-bound GroupNorm apply kernel and the fused tcgen05 attention forward
+    def _avg(kind, dims3):
+        sel = [o for o in prof if o["kind"] == kind and o["dims"][:3] == dims3]
+        return (sum(o["ms"] for o in sel) / len(sel), sel[0]) if sel else (None, None)
+    extra = {}
+    gms, g0 = _avg("gn_apply", [args.size, args.size, 256])
+    if gms:
+        extra["groupnorm"] = dict(bound="hbm", kernel=f"gn_apply_kernel (GroupNorm32 + scale-shift + SiLU, {args.size}x{args.size}x256, read + write)",
+                                  achieved=round(g0["bytes"] / gms / 1e6, 1), peak=peaks["hbm"], unit="GB/s",
+                                  frac=round(g0["bytes"] / gms / 1e6 / peaks["hbm"], 4), bytes_per_launch=g0["bytes"], ms_per_launch=round(gms, 4))
+    ams, a0 = _avg("attn_fwd", [(args.size // 8) ** 2, 512, 8])
+    if ams:
+        extra["attention"] = dict(bound="latency (tensor pipe far from saturated: 0.5 % of the step's FLOPs)",
+                                  kernel="tok_to_chan_kernel + flash_fwd_kernel (tcgen05 kind::tf32, L=1024, 8 heads x 64 ch)",
+                                  achieved=round(a0["flops"] / ams / 1e9, 1), peak=peaks["bf16_sustained"], unit="TFLOP/s",
+                                  frac=round(a0["flops"] / ams / 1e9 / peaks["bf16_sustained"], 4), ms_per_launch=round(ams, 4))
+    roofline["other_kernels"] = extra
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True,
                scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
                config=dict(workload=f"osmosis_sample_config.yaml, batch {B} per GPU, {args.size}x{args.size} RGBD, 1000-step guided "

@@ -47,7 +47,7 @@ inline void prefer_max_smem_once(K kernel, bool* done) {
 // so the NEXT kernel's CTAs are scheduled (and run their prologue) while this one drains, instead of paying a full launch
 // + drain gap at each of the ~800 kernel boundaries of a step.  pdl_wait() blocks until every prerequisite grid has
 // completed and its memory is visible, so data dependences are exactly those of plain stream order; nothing before it
-// touches global memory.  OSM_PDL=0 launches without the attribute (both instructions are then no-ops).
+// touches global memory.  Without the attribute (the default, see pdl_enabled) both instructions are no-ops.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
