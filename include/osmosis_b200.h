@@ -162,6 +162,17 @@ int osm_minmax_percentile(const float* img, float* out, int B, int n, float q_lo
 /* depth_tensor_to_color_image (utils.py:748-763): matplotlib-style lookup of img in [0,1] in a [256][3] table -> [B,3,n] */
 int osm_colormap(const float* img, const float* lut, float* out, int B, int n, void* stream);
 
+/* ------------------------------------------------------------ input pipeline ------------------------------
+ * Replaces the torchvision transform chain of osmosis_sampling.py:46-49 for one decoded image already in device memory:
+ * ToTensor -> Resize(size) [bilinear, antialias, short side -> size] -> CenterCrop([size, size]) -> Normalize(0.5, 0.5), and
+ * (degamma != 0) the de-gamma of osmosis_sampling.py:170-175, y <- 2 (0.5 (y + 1))^2.2 - 1.
+ *   src u8 [H][W][channels] with row_pitch_bytes between rows, channels 3 (RGB) or 1 (grey, replicated as .convert("RGB") does);
+ *   scratch >= 3 * H * size floats; out f32 [3][size][size] in [-1, 1].                                              */
+int osm_preprocess_image(const uint8_t* src, int H, int W, int channels, int row_pitch_bytes, float* scratch, float* out,
+                         int size, int degamma, void* stream);
+/* the de-gamma alone on n floats (in place allowed) */
+int osm_degamma(const float* y, float* out, long n, void* stream);
+
 /* ------------------------------------------------------------ layer-level entry points -----------------
  * Used by the kernel parity tests (tests/test_kernels_gpu.py); NHWC fp32 with an explicit pixel stride
  * `ld` (elements).  Not part of the sampling API.                                                     */

@@ -594,6 +594,71 @@ def ddpm_uncond_update(x, eps, z, alpha_t, alphabar_t, beta_tilde):
 # --------------------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------------------
+# input pipeline  (osmosis_sampling.py:46-49, 170-175; torchvision ToTensor / Resize / CenterCrop / Normalize)
+# --------------------------------------------------------------------------------------
+
+
+def _aa_weights(in_size: int, out_size: int):
+    """Taps of the antialiased bilinear (triangle) filter, as ATen computes them for float tensors
+    (aten/src/ATen/native/cpu/UpSampleKernel.cpp, `_compute_indices_min_size_weights_aa`, align_corners=False): float
+    variables combined with double literals, rounded where ATen stores a float."""
+    f32, f64 = np.float32, np.float64
+    scale = f32(in_size) / f32(out_size)
+    support = scale if scale >= 1 else f32(1.0)
+    invscale = f32(f64(1.0) / f64(scale)) if scale >= 1 else f32(1.0)
+    taps = []
+    for i in range(out_size):
+        center = f32(f64(scale) * (i + 0.5))
+        xmin = max(int(f64(center - support) + 0.5), 0)
+        xsize = min(int(f64(center + support) + 0.5), in_size) - xmin
+        w = np.zeros(xsize, dtype=f32)
+        total = f32(0)
+        for j in range(xsize):
+            x = f32((f64(f32(j + xmin) - center) + 0.5) * f64(invscale))
+            w[j] = max(f32(0), f32(1) - abs(x))
+            total = f32(total + w[j])
+        taps.append((xmin, (w / total).astype(f32)))
+    return taps
+
+
+def _aa_resize_axis(x: np.ndarray, axis: int, out_size: int, keep=None) -> np.ndarray:
+    """One separable pass; per tap one fused multiply-add in tap order (what the compiled ATen loop does)."""
+    x = np.moveaxis(x, axis, -1)
+    taps = _aa_weights(x.shape[-1], out_size)
+    lo, hi = keep if keep is not None else (0, out_size)
+    y = np.zeros(x.shape[:-1] + (hi - lo,), dtype=np.float32)
+    for i in range(lo, hi):
+        xmin, w = taps[i]
+        acc = x[..., xmin] * w[0]
+        for j in range(1, len(w)):
+            acc = (x[..., xmin + j].astype(np.float64) * np.float64(w[j]) + acc.astype(np.float64)).astype(np.float32)
+        y[..., i - lo] = acc
+    return np.moveaxis(y, -1, axis)
+
+
+def preprocess_image(img_u8: np.ndarray, size: int = 256, degamma: bool = False) -> np.ndarray:
+    """uint8 [H,W,3] (or [H,W] grey, replicated like PIL's .convert("RGB")) -> float32 [3,size,size] in [-1,1]:
+    ToTensor -> Resize(size) (bilinear, antialias, short side) -> CenterCrop -> Normalize(0.5, 0.5) of
+    osmosis_sampling.py:46-49, then the optional de-gamma of :170-175."""
+    a = np.asarray(img_u8)
+    if a.ndim == 2:
+        a = np.repeat(a[:, :, None], 3, axis=2)
+    H, W = a.shape[:2]
+    x = (a.astype(np.float32) / np.float32(255)).transpose(2, 0, 1)                  # ToTensor
+    if H <= W:
+        nh, nw = size, int(size * W / H)                                             # torchvision _compute_resized_output_size
+    else:
+        nh, nw = int(size * H / W), size
+    top, left = int(round((nh - size) / 2.0)), int(round((nw - size) / 2.0))         # CenterCrop (round half to even)
+    x = _aa_resize_axis(x, 2, nw, keep=(left, left + size))                          # horizontal pass first
+    x = _aa_resize_axis(x, 1, nh, keep=(top, top + size))
+    x = (x - np.float32(0.5)) / np.float32(0.5)                                      # Normalize
+    if degamma:
+        x = np.float32(2) * np.power(np.float32(0.5) * (x + np.float32(1)), np.float32(2.2)) - np.float32(1)
+    return x.astype(np.float32)
+
+
 def _floats(s):
     if isinstance(s, (int, float)):
         return (float(s),)

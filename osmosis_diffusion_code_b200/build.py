@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libosmosis_b200.so")
-SOURCES = ["capi.cu", "sampler_kernels.cu", "postprocess.cu", "norm.cu", "misc.cu", "attention.cu", "attention_flash.cu", "conv_simt.cu", "conv_tc.cu",
+SOURCES = ["capi.cu", "sampler_kernels.cu", "postprocess.cu", "preprocess.cu", "norm.cu", "misc.cu", "attention.cu", "attention_flash.cu", "conv_simt.cu", "conv_tc.cu",
            "unet_engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -196,5 +196,7 @@ int postprocess_launch(int op_kind, int depth_kind, const float* dv, const float
                        float* degraded, float* recon, float* norm_out, int B, int HW, cudaStream_t s);
 int minmax_quantile_launch(const float* img, float* out, int B, int n, float q_lo, float q_hi, float vmin, float vmax, cudaStream_t s);
 int colormap_launch(const float* img, const float* lut, float* out, int B, int n, cudaStream_t s);
+int preprocess_launch(const uint8_t* src, int H, int W, int Cs, int pitch, float* tmp, float* out, int S, int degamma, cudaStream_t s);
+int degamma_launch(const float* y, float* out, size_t n, cudaStream_t s);
 
 }  // namespace osm

@@ -203,7 +203,7 @@ class GaussianDiffusion:
             g_mo=torch.empty(B, 2 * Cc, H, W, **f32), g_unet=torch.zeros(B, Cc, H, W, **f32),
             zero_scale=torch.zeros(4, **f32),
             grad=torch.empty(B, Cc, H, W, **f32), losses=torch.zeros(B, 4, **f32),
-            scale=cond._scale4(Cc).to(dev), y=measurement.contiguous().float(),
+            scale=cond._scale4(Cc).to(dev), y=measurement.contiguous().float().clone(),
             clip=(cond.gradient_clip_value if cond.gradient_clip else -1.0))
 
     def fused_step(self, model, cond, st, img, noise):
@@ -243,35 +243,68 @@ class GaussianDiffusion:
         """`measurement` may live in (pinned) host memory: it is then streamed to the device every step.  `progress(idx,
         loss[B] numpy)` is called after every step when given - it costs one device->host read per step, which is what
         the reference's progress bar does (gaussian_diffusion.py:276-296)."""
-        img = x_start.detach().clone().contiguous().float()
         host_meas = None
         if not measurement.is_cuda:
             host_meas = measurement.contiguous().float()
             if not host_meas.is_pinned():
                 host_meas = host_meas.pin_memory()
-            measurement = torch.empty(host_meas.shape, dtype=torch.float32, device=img.device)
-            measurement.copy_(host_meas, non_blocking=True)
-        stepper = FusedStepper(self, model, cond, img, measurement, sample_pattern, noise_mode=noise_mode, cuda_graph=cuda_graph)
-        st = stepper.st
-        for idx in idxs:
+        stepper = self._stepper_for(model, cond, x_start, measurement if host_meas is None else host_meas, sample_pattern,
+                                    noise_mode, cuda_graph)
+        st, img = stepper.st, stepper.img
+        # progress read-back is deferred by one step: the loss of step k is copied to a pinned slot on the stream and
+        # handed to the callback after step k+1 has been enqueued, so the device never waits for the host.
+        pend, slots, slot_ev = None, None, None
+        if progress is not None:
+            slots = [torch.empty(st["losses"].shape[0], dtype=torch.float32).pin_memory() for _ in range(2)]
+            slot_ev = [torch.cuda.Event() for _ in range(2)]
+        for k, idx in enumerate(idxs):
             if host_meas is not None:
                 st["y"].copy_(host_meas, non_blocking=True)
             # alternate length M of the gibbsDDRM-style pattern (gaussian_diffusion.py:224-227): M full steps at this index
             for _ in range(utilso.set_alternate_length(sample_pattern, idx, self.num_timesteps)):
                 stepper.step(idx)
             if progress is not None:
-                progress(idx, st["losses"][:, 0].cpu().numpy())
+                slots[k & 1].copy_(st["losses"][:, 0], non_blocking=True)
+                slot_ev[k & 1].record()
+                if pend is not None:
+                    slot_ev[pend[0]].synchronize()
+                    progress(pend[1], slots[pend[0]].numpy().copy())
+                pend = (k & 1, idx)
             # `record` (gaussian_diffusion.py:310-326): keep pred_xstart of image 0 every record_every steps.  The snapshot
             # is a device-to-device copy on the stream (no host sync in the loop); images are built after the loop.
             if record is not None and ((idx % record["record_every"] == 0) or (idx == 0) or (idx == 999)):
                 record.setdefault("frames", []).append(st["x0"][0:1].clone())
+        if pend is not None:
+            slot_ev[pend[0]].synchronize()
+            progress(pend[1], slots[pend[0]].numpy().copy())
         if record is not None:
             self.last_record = self._finish_record(record)
         variable_dict = cond.operator.optimize(freeze_phi=True)
         loss = st["losses"][:, 0].cpu().numpy()
         self.last_gradients = st["grad"]
         self.last_aux = st["losses"]
-        return img, variable_dict, loss, st["x0"].detach().cpu()
+        return img.clone(), variable_dict, loss, st["x0"].detach().cpu()
+
+    def _stepper_for(self, model, cond, x_start, measurement, sample_pattern, noise_mode, cuda_graph):
+        """One FusedStepper (device state + captured CUDA graph) per (model, conditioner, batch shape): consecutive
+        `p_sample_loop` calls - the reference's per-image loop, `osmosis_sampling.py:117-199` - reuse the captured graph and
+        only refresh the image, the measurement and the step scalars."""
+        cache = self.__dict__.setdefault("_steppers", {})
+        key = (id(model), id(cond), tuple(x_start.shape), str(x_start.device), noise_mode, bool(cuda_graph),
+               tuple(sorted((k, str(v)) for k, v in (sample_pattern or {}).items())))
+        stepper = cache.get(key)
+        if stepper is None:
+            img = x_start.detach().clone().contiguous().float()
+            y = torch.empty(measurement.shape, dtype=torch.float32, device=img.device)
+            y.copy_(measurement, non_blocking=True)
+            stepper = FusedStepper(self, model, cond, img, y, sample_pattern, noise_mode=noise_mode, cuda_graph=cuda_graph)
+            while len(cache) >= 2:
+                cache.pop(next(iter(cache)))
+            cache[key] = stepper
+        else:
+            stepper.img.copy_(x_start.detach())
+            stepper.st["y"].copy_(measurement, non_blocking=True)
+        return stepper
 
     @staticmethod
     def _finish_record(record):

@@ -1,6 +1,7 @@
 """Seeded inputs shared by tests/golden/make_golden.py (which runs the reference) and the parity tests."""
 import zlib
 
+import numpy as np
 import torch
 
 from osmosis_diffusion_code_b200.synthetic import synth_measurement
@@ -60,3 +61,36 @@ def post_inputs(name: str) -> torch.Tensor:
     if name.startswith("ties"):
         return torch.round(torch.randn(1, H, W, generator=g) * 2) / 4
     return torch.full((1, H, W), 0.25)
+
+
+# input-pipeline cases: (H, W, seed, kind).  Seeded uint8 images: down-scale (landscape / portrait), identity, up-scale,
+# a large down-scale with long filters, and a smooth photo-like image; "grey" is a single-channel depth map.
+PRE_CASES = {"land300x400": (300, 400, 21, "noise"), "port517x389": (517, 389, 22, "noise"), "same256": (256, 256, 23, "noise"),
+             "up200x320": (200, 320, 24, "noise"), "big720x1280": (720, 1280, 25, "smooth"), "odd257x511": (257, 511, 26, "smooth"),
+             "grey300x333": (300, 333, 27, "grey")}
+
+
+def pre_inputs(name: str) -> np.ndarray:
+    H, W, seed, kind = PRE_CASES[name]
+    rs = np.random.RandomState(seed)
+    if kind == "noise":
+        return rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    ch = 1 if kind == "grey" else 3
+    low = torch.from_numpy(rs.rand(1, ch, 12, 16).astype(np.float32))
+    img = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)[0].clamp(0, 1)
+    img = (img * 255).round().to(torch.uint8).permute(1, 2, 0).numpy()
+    img = np.ascontiguousarray(img + (rs.randint(0, 3, img.shape).astype(np.uint8)))  # a little sensor noise (wraps are fine)
+    return img[:, :, 0] if kind == "grey" else img
+
+
+FULL_CASE = "land300x400"   # stored in full in pre_golden.npz; the other cases as every 3rd pixel + checksums
+
+
+def pre_check(gold, key, got: np.ndarray, atol: float):
+    """Compares `got` [3,256,256] with the golden entry `key` (full, or sub-sampled + checksum)."""
+    if key in gold.files:
+        return float(np.abs(got - gold[key]).max()) <= atol
+    sub, sums = gold[key + "|sub3"], gold[key + "|sum"]
+    ok = float(np.abs(got[:, ::3, ::3] - sub).max()) <= atol
+    g64 = got.astype(np.float64)
+    return ok and abs(g64.sum() - sums[0]) <= atol * got.size and abs(np.abs(g64).sum() - sums[1]) <= atol * got.size

@@ -352,3 +352,36 @@ def test_loop_guidance_window_and_alternate_length_vs_oracle():
         assert float(d.max()) < 0.2
         for n, p in zip(names, pho):
             assert maxdiff(getattr(op, n).cpu(), p) < 1e-4
+
+
+def test_loop_reuse_and_host_measurement_progress():
+    """Consecutive p_sample_loop calls on one sampler reuse the captured step graph (the reference's per-image loop,
+    osmosis_sampling.py:117-199): the second call must give the bits of a fresh sampler.  The measurement comes from host
+    memory and the progress callback sees every step once, in order, with the loss the loop finally returns."""
+    cname = "osmosis"
+    y, _ = case_inputs("meas:" + cname)
+    m = model("fp32")
+
+    def run(sampler, cfg, cond, seen):
+        torch.manual_seed(cfg["manual_seed"])
+        x_start = torch.randn(1, 4, *y.shape[2:], device=DEV)
+        out = sampler.p_sample_loop(model=m, x_start=x_start, measurement=y.clone(), measurement_cond_fn=cond.conditioning,
+                                    record=False, save_root=None, pretrain_model="osmosis", rgb_guidance=False,
+                                    sample_pattern=cfg["sample_pattern"], progress=lambda idx, loss: seen.append((idx, loss.copy())))
+        torch.cuda.synchronize()
+        return out
+
+    cfg, op, cond, sampler = _native_objects(cname, 1)
+    phi0 = {n: getattr(op, n).clone() for n in op.groups}
+    seen1, seen2 = [], []
+    img1, vd1, loss1, x01 = run(sampler, cfg, cond, seen1)
+    for n in op.groups:                       # same operator object, phi restored in place: the graph's pointers stay valid
+        getattr(op, n).data.copy_(phi0[n])
+    img2, vd2, loss2, x02 = run(sampler, cfg, cond, seen2)
+    assert len(sampler._steppers) == 1
+    assert torch.equal(img1, img2) and torch.equal(x01, x02) and np.array_equal(loss1, loss2)
+    T = sampler.num_timesteps
+    assert [i for i, _ in seen1] == list(range(T))[::-1] == [i for i, _ in seen2]
+    assert np.array_equal(seen1[-1][1], loss1)
+    for (_, a), (_, b) in zip(seen1, seen2):
+        assert np.array_equal(a, b)
