@@ -94,3 +94,15 @@ def pre_check(gold, key, got: np.ndarray, atol: float):
     ok = float(np.abs(got[:, ::3, ::3] - sub).max()) <= atol
     g64 = got.astype(np.float64)
     return ok and abs(g64.sum() - sums[0]) <= atol * got.size and abs(np.abs(g64).sum() - sums[1]) <= atol * got.size
+
+
+# `ps` / rgb_guidance path (rgb_guidance_sample_config.yaml) and the `mse` loss variant of the osmosis conditioning
+PS_CASE = dict(yaml="rgb_guidance_sample_config.yaml", respacing=6, step_idx=[5, 2, 0], step_seed=31)
+MSE_CASE = dict(yaml="osmosis_sample_config.yaml", respacing=6, step_idx=[5, 2])
+
+
+def ps_measurement():
+    """A smooth RGB guide image in [-1, 1], [1,3,32,32] (the rgb_guidance demo guides the RGB channels towards an image)."""
+    g = _gen("ps:meas")
+    low = torch.rand(1, 3, 4, 4, generator=g)
+    return (2 * torch.nn.functional.interpolate(low, size=SMALL_HW, mode="bilinear", align_corners=False) - 1).contiguous()
