@@ -88,7 +88,7 @@ int osm_unet_profile_ops(osm_unet_t h, int which, void* stream, int cap, float* 
 
 /* ------------------------------------------------------------- sampler elementwise ---------------------
  * coef: [T][8] fp32 rows = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
- * posterior_mean_coef2, log(beta), posterior_log_variance_clipped, 0, 0}, each the fp32 rounding of the
+ * posterior_mean_coef2, log(beta), posterior_log_variance_clipped, alphas_cumprod, alphas_cumprod_prev}, each the fp32 rounding of the
  * reference's float64 table entry (posterior_mean_variance.py:265-269).  t_idx[B]: int32 respaced index. */
 
 /* replaces EpsilonXMeanProcessor.get_mean_and_xstart (posterior_mean_variance.py:104-136) and
@@ -100,6 +100,14 @@ int osm_posterior_fwd(const float* coef, const int32_t* t_idx, const float* x, c
  * g_x [B,C,HW] (direct path through x), g_model_out [B,2C,HW].                                        */
 int osm_posterior_vjp(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean,
                       const float* g_logvar, float* g_x, float* g_model_out, int B, int C, int HW, void* stream);
+/* The same two with `clip_denoised` (MeanProcessor.process_xstart, posterior_mean_variance.py:41-50): x0 is clamped to
+ * [-1, 1] before the posterior mean; the VJP recomputes the unclamped x0 from x / model_out (both NULL = no clamp) and
+ * passes the gradient only where it lay inside [-1, 1], as torch's clamp backward does.                            */
+int osm_posterior_fwd_ex(const float* coef, const int32_t* t_idx, const float* x, const float* model_out, float* x0,
+                         float* mean, float* logvar, int B, int C, int HW, int clip_denoised, void* stream);
+int osm_posterior_vjp_ex(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean,
+                         const float* g_logvar, float* g_x, float* g_model_out, int B, int C, int HW, const float* x,
+                         const float* model_out, void* stream);
 /* replaces condition_methods.py:211-223 + gaussian_diffusion.py:266-271:
  *   x_out = mean - scale[c] * clamp(g_a + g_b, +-clip) + [t_idx != 0] * exp(0.5*logvar) * noise
  * g_b may be NULL; clip < 0 disables clamping.  The clamped-before-scale raw gradient g_a+g_b is written to
@@ -107,6 +115,20 @@ int osm_posterior_vjp(const float* coef, const int32_t* t_idx, const float* g_x0
 int osm_sampler_update(const float* mean, const float* g_a, const float* g_b, const float* scale4, float clip,
                        const float* logvar, const float* noise, const int32_t* t_idx, float* x_out, float* grad_out,
                        int B, int C, int HW, void* stream);
+/* osm_sampler_update with the order of the rgb_guidance branch (noise_first != 0): DDPM.p_sample adds the noise
+ * (gaussian_diffusion.py:499-501), then the `ps` conditioning subtracts scale * gradient (condition_methods.py:248):
+ *   x_out = (mean + [t_idx != 0] * exp(0.5*logvar) * noise) - clamp(g_a + g_b) * scale[c]                          */
+int osm_sampler_update_ex(const float* mean, const float* g_a, const float* g_b, const float* scale4, float clip,
+                          const float* logvar, const float* noise, const int32_t* t_idx, float* x_out, float* grad_out,
+                          int B, int C, int HW, int noise_first, void* stream);
+/* replaces DDIM.p_sample after p_mean_variance (gaussian_diffusion.py:506-535): eps from (x, pred_xstart x0), sigma from
+ * eta and the alphas_cumprod columns of coef, out = x0 sqrt(abar_prev) + sqrt(1 - abar_prev - sigma^2) eps + [t != 0] sigma z */
+int osm_ddim_sample(const float* coef, const int32_t* t_idx, const float* x, const float* x0, const float* noise, float eta,
+                    float* out, int B, int C, int HW, void* stream);
+/* replaces ConditioningMethod.grad_and_value (gaussian branch, condition_methods.py:36-40) for the identity
+ * `rgb_guidance` operator (measurements.py:80-97), per image: losses[b] = || y_b - x0_b[:3] ||_2 and
+ * g_x0 [B,C,HW] = d losses[b] / d x0 (zero for channels >= 3).  y [B,3,HW].                                         */
+int osm_ps_guidance(const float* x0, const float* y, float* g_x0, float* losses, int B, int C, int HW, void* stream);
 /* replaces osmosis_utils/diffusion.py:122 (GaussianDiffusion.inverse, unguided ancestral update):
  *   x = (x - c_eps * eps) * c_x + c_z * z   with eps = model_out[:, :C]                               */
 int osm_ddpm_uncond_update(float* x, const float* model_out, const float* z, float c_x, float c_eps, float c_z, int B,
@@ -120,6 +142,9 @@ int osm_ddpm_uncond_update(float* x, const float* model_out, const float* z, flo
 #define OSM_DEPTH_GAMMA 1           /* utils.py:557-558  ((d+v0)*v1)^v2                                 */
 #define OSM_DEPTH_MOVE 2            /* utils.py:554-555  d+v0                                           */
 
+#define OSM_LOSS_NORM 0             /* condition_methods.py:127-130  ||r||_2                            */
+#define OSM_LOSS_MSE 1              /* condition_methods.py:133-138  mean(r^2) per image                */
+
 typedef struct osm_guidance_params {
   int op_kind;           /* OSM_OP_*                                                                    */
   int depth_kind;        /* OSM_DEPTH_* of the operator                                                 */
@@ -131,6 +156,7 @@ typedef struct osm_guidance_params {
   int n_iter;            /* inner iterations when not frozen (sample_pattern.n_iter)                    */
   float gamma_avrg;      /* aux_loss.avrg_loss weight, 0 if absent (losses.py:29-45)                    */
   float gamma_val;       /* aux_loss.val_loss weight, 0 if absent  (losses.py:51-62)                    */
+  int loss_kind;         /* OSM_LOSS_NORM / OSM_LOSS_MSE: loss_function (condition_methods.py:127-138)  */
 } osm_guidance_params;
 
 /* replaces Operator.forward (measurements.py:138-151, 251-264, 363-376): out[B,3,HW] = A_phi(x[B,4,HW]).

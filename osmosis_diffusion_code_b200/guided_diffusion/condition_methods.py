@@ -2,9 +2,10 @@
 
 Mirrors the reference `guided_diffusion/condition_methods.py`: the registry (:8-24), `ConditioningMethod`
 (:27-58) and `PosteriorSamplingOsmosis` / name `osmosis` (:61-231) with the options the shipped configs
-select: `loss_function: norm`, `loss_weight: depth | none`, `gradient_x_prev: True`, gradient clipping, the
-auxiliary losses and the pcgs sampling pattern.  The `ps` method, the `mse` loss and `gradient_x_prev: False`
-are outside the hot path and raise NotImplementedError.
+select: `loss_function: norm | mse`, `loss_weight: depth | none`, `gradient_x_prev: True`, gradient clipping, the
+auxiliary losses and the pcgs sampling pattern; and `PosteriorSampling` / name `ps` (:234-251), plain DPS with the
+gaussian branch of `ConditioningMethod.grad_and_value` (:36-40) - what rgb_guidance_sample_config.yaml selects.
+`gradient_x_prev: False` raises (it does inside the reference too); the poisson branch (:42-48) is not built.
 
 What the reference does in ~66 small ATen kernels and 3 device->host syncs per inner iteration
 (grad_and_value :109-144, AuxiliaryLoss, backward, operator.optimize) is ONE launch here
@@ -76,10 +77,13 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
         clip = [s for s in kwargs.get("gradient_clip", "False").split(",")]
         self.gradient_clip = utilso.str2bool(clip[0])
         self.gradient_clip_value = float(clip[1].strip()) if self.gradient_clip else None
-        if self.loss_function != "norm":
-            raise NotImplementedError("only loss_function 'norm' is on the native path")
+        if self.loss_function not in ("norm", "mse"):
+            raise NotImplementedError                       # as the reference does at call time (:140-142)
         if not self.gradient_x_prev:
-            raise NotImplementedError("gradient_x_prev: False is not on the native path")
+            # the reference's branch cannot run: it detaches x_0_hat, switches x_prev.requires_grad off and then calls
+            # total_loss.backward(inputs=[x_prev]) (:152-156, :186-191), which torch rejects
+            raise NotImplementedError("gradient_x_prev: False raises inside the reference as well (backward w.r.t. a tensor "
+                                      "that does not require grad)")
         self._params = None
         self._dev = {}
 
@@ -109,6 +113,7 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
             p.n_iter = int(self.n_iter)
             w = self.aux_loss.kernel_weights() if self.aux_loss is not None else {"gamma_avrg": 0.0, "gamma_val": 0.0}
             p.gamma_avrg, p.gamma_val = w["gamma_avrg"], w["gamma_val"]
+            p.loss_kind = 1 if self.loss_function == "mse" else 0
             self._params = p
         return self._params
 
@@ -165,3 +170,53 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
             cols = {"avrg_loss": 1, "val_loss": 2}
             aux_loss_dict = {k: losses[:, cols[k]].clone() for k in self.aux_loss.losses_dictionary}
         return x_t, sep_loss, variables_dict, grad, aux_loss_dict
+
+
+@register_conditioning_method(name="ps")
+class PosteriorSampling(ConditioningMethod):
+    """condition_methods.py:234-251: x_t <- x_t - scale_c * d||y - A(x_0_hat[:, :3])||_2 / d x_prev with a parameter-free
+    operator.  Native for the identity operators (`rgb_guidance`, `noise`): the norm and its gradient w.r.t. x_0_hat are ONE
+    launch (osm_ps_guidance); the gradient then flows to x_prev through whatever produced x_0_hat (the native UNet's
+    input-VJP).  Per-image norm: a batch of B is B independent reference runs (the reference takes one norm over the
+    whole batch, which couples the images; it is only ever run at B = 1)."""
+
+    def __init__(self, operator, noiser, **kwargs):
+        super().__init__(operator, noiser)
+        self.scale = torch.tensor(_parse_scale(kwargs.get("scale", 1.0)))
+        if getattr(noiser, "__name__", "gaussian") not in ("gaussian", "clean"):
+            raise NotImplementedError("the `ps` conditioning is built for the gaussian branch (condition_methods.py:36-40)")
+        if not getattr(operator, "is_identity", False) and not type(operator).__name__ == "DenoiseOperator":
+            raise NotImplementedError("the native `ps` conditioning supports the identity operators (rgb_guidance, noise)")
+        self._dev = {}
+
+    _scale4 = PosteriorSamplingOsmosis._scale4
+
+    def guidance_gradient(self, x_0_hat, measurement, g_x0, losses):
+        B, Cc, H, W = x_0_hat.shape
+        _lib.check(_lib.load().osm_ps_guidance(_lib.ptr(x_0_hat), _lib.ptr(measurement), _lib.ptr(g_x0), _lib.ptr(losses), B, Cc,
+                                               H * W, _lib.stream()))
+
+    def grad_and_value(self, x_prev, x_0_hat, measurement, **kwargs):
+        x0 = x_0_hat.detach().contiguous()
+        g_x0 = torch.empty_like(x0)
+        losses = torch.empty(x0.shape[0], dtype=torch.float32, device=x0.device)
+        self.guidance_gradient(x0, measurement.contiguous().float(), g_x0, losses)
+        if x_prev.grad is not None:
+            x_prev.grad = None
+        torch.autograd.backward([x_0_hat], [g_x0], inputs=[x_prev])
+        return x_prev.grad, losses
+
+    def conditioning(self, x_prev, x_t, x_0_hat, measurement, **kwargs):
+        norm_grad, norm = self.grad_and_value(x_prev=x_prev, x_0_hat=x_0_hat, measurement=measurement, **kwargs)
+        B, Cc, H, W = x_t.shape
+        key = (str(x_t.device), B, Cc)
+        if key not in self._dev:
+            self._dev = {key: dict(zero_t=torch.zeros(B, dtype=torch.int32, device=x_t.device), scale=self._scale4(Cc).to(x_t.device))}
+        buf = self._dev[key]
+        with torch.no_grad():
+            xt = x_t.detach().contiguous()
+            # x_t -= grad * scale: the update kernel with clamping and the noise term switched off
+            _lib.check(_lib.load().osm_sampler_update_ex(_lib.ptr(xt), _lib.ptr(norm_grad.contiguous()), None, _lib.ptr(buf["scale"]),
+                                                         -1.0, _lib.ptr(xt), _lib.ptr(xt), _lib.ptr(buf["zero_t"]), _lib.ptr(xt), None,
+                                                         B, Cc, H * W, 1, _lib.stream()))
+        return xt, (norm[0] if B == 1 else norm)

@@ -146,7 +146,8 @@ class GaussianDiffusion:
         if model_output.shape[1] != 2 * x.shape[1]:
             raise NotImplementedError("the native posterior kernel expects a learned-variance model (2C output channels)")
         coef = self.mean_processor.table.on(x.device)
-        x0, mean, logvar = PosteriorFn.apply(x, model_output, coef, t.to(torch.int32).contiguous())
+        x0, mean, logvar = PosteriorFn.apply(x, model_output, coef, t.to(torch.int32).contiguous(),
+                                             self.mean_processor.clip_denoised)
         return {"mean": mean, "variance": torch.exp(logvar.detach()), "log_variance": logvar, "pred_xstart": x0}
 
     def p_sample(self, model, x, t):
@@ -158,13 +159,24 @@ class GaussianDiffusion:
 
     def p_sample_loop(self, model, x_start, measurement, measurement_cond_fn, record, save_root, pretrain_model=None,
                       image_idx=None, record_every=150, rgb_guidance=False, sample_pattern=None, **kwargs):
-        if pretrain_model != "osmosis" or rgb_guidance:
-            raise NotImplementedError("only the osmosis guided path (pretrain_model='osmosis', rgb_guidance=False) is native")
         if not x_start.is_cuda:
             raise _lib.OsmError("p_sample_loop needs CUDA tensors (no CPU fallback)")
-        from .condition_methods import PosteriorSamplingOsmosis
+        from .condition_methods import PosteriorSamplingOsmosis, PosteriorSampling
         from .unet import UNetModel
         cond = getattr(measurement_cond_fn, "__self__", None)
+        if pretrain_model != "osmosis" or rgb_guidance:
+            # "almost original dps code - rgb_guidance" (gaussian_diffusion.py:232-233, 299-306): p_sample, then the `ps`
+            # conditioning; returns only the image (:339-340)
+            idxs = list(range(self.num_timesteps))[::-1]
+            if kwargs.get("max_steps") is not None:
+                idxs = idxs[:kwargs["max_steps"]]
+            fused = (isinstance(model, UNetModel) and isinstance(cond, PosteriorSampling)
+                     and getattr(measurement_cond_fn, "__func__", None) is PosteriorSampling.conditioning
+                     and kwargs.get("fused", True))
+            if fused:
+                return self._loop_fused_ps(model, cond, x_start, measurement, idxs, kwargs.get("noise_mode", "batch"),
+                                           kwargs.get("progress"), kwargs.get("cuda_graph", True))
+            return self._loop_autograd_ps(model, measurement_cond_fn, x_start, measurement, idxs)
         fused = (isinstance(model, UNetModel) and isinstance(cond, PosteriorSamplingOsmosis)
                  and getattr(measurement_cond_fn, "__func__", None) is PosteriorSamplingOsmosis.conditioning
                  and kwargs.get("fused", True))
@@ -201,10 +213,11 @@ class GaussianDiffusion:
             mean=torch.empty(B, Cc, H, W, **f32), logvar=torch.empty(B, Cc, H, W, **f32),
             g_x0=torch.empty(B, Cc, H, W, **f32), g_direct=torch.zeros(B, Cc, H, W, **f32),
             g_mo=torch.empty(B, 2 * Cc, H, W, **f32), g_unet=torch.zeros(B, Cc, H, W, **f32),
-            zero_scale=torch.zeros(4, **f32),
+            zero_scale=torch.zeros(4, **f32), t_zero=torch.zeros(B, dtype=torch.int32, device=dev),
+            ps_loss=torch.zeros(B, **f32),
             grad=torch.empty(B, Cc, H, W, **f32), losses=torch.zeros(B, 4, **f32),
             scale=cond._scale4(Cc).to(dev), y=measurement.contiguous().float().clone(),
-            clip=(cond.gradient_clip_value if cond.gradient_clip else -1.0))
+            clip=(cond.gradient_clip_value if getattr(cond, "gradient_clip", False) else -1.0))
 
     def fused_step(self, model, cond, st, img, noise):
         """One guided reverse step on device buffers; `img` is updated in place.  No host synchronisation."""
@@ -237,6 +250,67 @@ class GaussianDiffusion:
         _lib.check(L.osm_sampler_update(_lib.ptr(st["mean"]), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
                                         _lib.ptr(st["zero_scale"]), -1.0, _lib.ptr(st["logvar"]), _lib.ptr(noise),
                                         _lib.ptr(st["t_idx"]), _lib.ptr(img), None, B, Cc, HW, s))
+
+    # DDIM's eta (gaussian_diffusion.py:507); None = this sampler is ancestral (DDPM.p_sample, :494-503)
+    ddim_eta = None
+
+    def fused_step_ps(self, model, cond, st, img, noise):
+        """One step of the rgb_guidance branch on device buffers: p_sample (DDPM or DDIM, with clip_denoised when the
+        sampler asks for it), the `ps` norm gradient, the UNet input-VJP, and x_t <- sample - scale * grad."""
+        L = _lib.load()
+        B, Cc, H, W = img.shape
+        HW = H * W
+        s = _lib.stream()
+        clip = int(self.mean_processor.clip_denoised)
+        model._forward_raw(img, st["t_model"], out=st["model_out"])
+        _lib.check(L.osm_posterior_fwd_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
+                                          _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, clip, s))
+        base, t_noise = st["mean"], st["t_idx"]
+        if self.ddim_eta is not None:   # the DDIM sample replaces mean + sigma z; the update kernel then adds no noise
+            _lib.check(L.osm_ddim_sample(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["x0"]),
+                                         _lib.ptr(noise), float(self.ddim_eta), _lib.ptr(st["mean"]), B, Cc, HW, s))
+            t_noise = st["t_zero"]
+        cond.guidance_gradient(st["x0"], st["y"], st["g_x0"], st["ps_loss"])
+        _lib.check(L.osm_posterior_vjp_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(st["g_x0"]), None, None,
+                                          _lib.ptr(st["g_direct"]), _lib.ptr(st["g_mo"]), B, Cc, HW,
+                                          _lib.ptr(img) if clip else None, _lib.ptr(st["model_out"]) if clip else None, s))
+        model._vjp_raw(st["g_mo"], grad_x=st["g_unet"])
+        _lib.check(L.osm_sampler_update_ex(_lib.ptr(base), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
+                                           _lib.ptr(st["scale"]), -1.0, _lib.ptr(st["logvar"]), _lib.ptr(noise),
+                                           _lib.ptr(t_noise), _lib.ptr(img), _lib.ptr(st["grad"]), B, Cc, HW, 1, s))
+
+    def _loop_fused_ps(self, model, cond, x_start, measurement, idxs, noise_mode, progress=None, cuda_graph=True):
+        host_meas = None
+        if not measurement.is_cuda:
+            host_meas = measurement.contiguous().float()
+            if not host_meas.is_pinned():
+                host_meas = host_meas.pin_memory()
+        stepper = self._stepper_for(model, cond, x_start, measurement if host_meas is None else host_meas, None, noise_mode,
+                                    cuda_graph)
+        st = stepper.st
+        for idx in idxs:
+            if host_meas is not None:
+                st["y"].copy_(host_meas, non_blocking=True)
+            stepper.step(idx)
+            if progress is not None:
+                progress(idx, st["ps_loss"].cpu().numpy())
+        self.last_loss = st["ps_loss"]
+        self.last_gradients = st["grad"]
+        self.last_pred_xstart = st["x0"]
+        return stepper.img.clone()
+
+    def _loop_autograd_ps(self, model, measurement_cond_fn, x_start, measurement, idxs):
+        img = x_start
+        for idx in idxs:
+            time = torch.tensor([idx] * img.shape[0], device=img.device)
+            img = img.requires_grad_()
+            out = self.p_sample(x=img, t=time, model=model)
+            noisy_measurement = self.q_sample(measurement, t=time)     # dead draw, after p_sample's (:241)
+            img, loss = measurement_cond_fn(x_t=out["sample"], measurement=measurement, noisy_measurement=noisy_measurement,
+                                            x_prev=img, x_0_hat=out["pred_xstart"])
+            img = img.detach_()
+            self.last_loss = loss
+        return img
 
     def _loop_fused(self, model, cond, x_start, measurement, sample_pattern, idxs, noise_mode, progress=None, cuda_graph=True,
                     record=None):
@@ -368,6 +442,8 @@ class FusedStepper:
         self.st = sampler.fused_state(model, cond, img, measurement)
         self.noise = torch.empty_like(img)
         self.dead = torch.empty_like(self.st["y"])
+        from .condition_methods import PosteriorSampling
+        self.ps = isinstance(cond, PosteriorSampling)   # rgb_guidance branch: p_sample + `ps` conditioning
         self.use_graph = bool(cuda_graph)
         self.graph = None
         self.graph_unguided = None
@@ -382,6 +458,22 @@ class FusedStepper:
 
     def step(self, idx, freeze=None):
         s, st, T = self.sampler, self.st, self.sampler.num_timesteps
+        if self.ps:
+            st["t_idx"].fill_(idx)
+            st["t_model"].fill_(s._model_timestep(idx))
+            self._draw_into(self.noise)    # p_sample's draw comes first in this branch (gaussian_diffusion.py:498 / :522),
+            self._draw_into(self.dead)     # then the dead q_sample draw (:241)
+            if self.use_graph and self.calls >= 1:
+                if self.graph is None:
+                    torch.cuda.synchronize()
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph):
+                        s.fused_step_ps(self.model, self.cond, st, self.img, self.noise)
+                self.graph.replay()
+            else:
+                s.fused_step_ps(self.model, self.cond, st, self.img, self.noise)
+            self.calls += 1
+            return
         guided = s._guidance_on(self.sample_pattern, idx)
         if freeze is None:
             freeze = utilso.is_freeze_phi(self.sample_pattern, idx, T)
@@ -475,3 +567,27 @@ class DDPM(SpacedDiffusion):
         if t[0] != 0:
             sample = sample + torch.exp(0.5 * out["log_variance"]) * noise
         return {"sample": sample, "pred_xstart": out["pred_xstart"]}
+
+
+@register_sampler(name="ddim")
+class DDIM(SpacedDiffusion):
+    """gaussian_diffusion.py:505-535.  In the fused loop the sample is one kernel (osm_ddim_sample); `p_sample` below is the
+    reference-facing, autograd-compatible form of the same arithmetic."""
+    ddim_eta = 0.0
+
+    def p_sample(self, model, x, t, eta=0.0):
+        out = self.p_mean_variance(model, x, t)
+        L = _lib.load()
+        B, Cc, H, W = x.shape
+        noise = torch.randn_like(x)
+        sample = torch.empty_like(out["pred_xstart"])
+        coef = self.mean_processor.table.on(x.device)
+        _lib.check(L.osm_ddim_sample(_lib.ptr(coef), _lib.ptr(t.to(torch.int32).contiguous()), _lib.ptr(x.detach().contiguous()),
+                                     _lib.ptr(out["pred_xstart"].detach().contiguous()), _lib.ptr(noise), float(eta),
+                                     _lib.ptr(sample), B, Cc, H * W, _lib.stream()))
+        return {"sample": sample, "pred_xstart": out["pred_xstart"]}
+
+    def predict_eps_from_x_start(self, x_t, t, pred_xstart):
+        coef1 = extract_and_expand(self.sqrt_recip_alphas_cumprod, t, x_t)
+        coef2 = extract_and_expand(self.sqrt_recipm1_alphas_cumprod, t, x_t)
+        return (coef1 * x_t - pred_xstart) / coef2

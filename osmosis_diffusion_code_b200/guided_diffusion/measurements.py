@@ -3,7 +3,8 @@
 Mirrors the registries and classes of the reference `guided_diffusion/measurements.py`:
 `get_operator` (:30-38, also stamps `__name__`), `HazePhysicalOperator` (:107-208),
 `UnderWaterPhysicalRevisedOperator` (:211-329), `UnderWaterPhysicalOperator` (:332-433), `get_noise`
-(:454-459), `Clean` (:471-474).
+(:454-459), `Clean` (:471-474), `GaussianNoise` (:477-483), and the parameter-free `DenoiseOperator` (:61-77) /
+`RGBGuidanceOperator` (:80-97) of the rgb_guidance demo.
 
 Difference in mechanics, not in results: the water parameters of all images live in ONE device tensor
 `phi[B, 9] = {a | b | inf}` that the fused guidance kernel (osm_guidance_phi_loop) reads and updates in place;
@@ -43,6 +44,53 @@ def get_operator(name: str, **kwargs):
     operator = __OPERATOR__[name](**kwargs)
     operator.__name__ = name
     return operator
+
+
+class LinearOperator:
+    """measurements.py:41-58: operators without parameters."""
+
+    def forward(self, data, **kwargs):
+        raise NotImplementedError
+
+    def transpose(self, data, **kwargs):
+        raise NotImplementedError
+
+    def ortho_project(self, data, **kwargs):
+        return data - self.transpose(self.forward(data, **kwargs), **kwargs)
+
+    def project(self, data, measurement, **kwargs):
+        return self.ortho_project(measurement, **kwargs) - self.forward(data, **kwargs)
+
+
+@register_operator(name="noise")
+class DenoiseOperator(LinearOperator):
+    """measurements.py:61-77: identity."""
+
+    def __init__(self, device, **kwargs):
+        self.device = device
+
+    def forward(self, data, **kwargs):
+        return data
+
+    def transpose(self, data):
+        return data
+
+    def ortho_project(self, data):
+        return data
+
+    def project(self, data):
+        return data
+
+
+@register_operator(name="rgb_guidance")
+class RGBGuidanceOperator(DenoiseOperator):
+    """measurements.py:80-97: identity on the RGB channels the `ps` conditioning hands it.  The fused loop recognises it
+    (`is_identity`) and runs osm_ps_guidance, which has the operator folded in."""
+    is_identity = True
+
+    def __init__(self, device, batch_size=1, **kwargs):
+        self.device = device
+        self.batch_size = batch_size
 
 
 def depth_spec(depth_type, value):
@@ -193,3 +241,14 @@ class Noise:
 class Clean(Noise):
     def forward(self, data):
         return data
+
+
+@register_noise(name="gaussian")
+class GaussianNoise(Noise):
+    """measurements.py:477-483: y + sigma * randn (drawn once per image, before the sampling loop is seeded)."""
+
+    def __init__(self, sigma):
+        self.sigma = sigma
+
+    def forward(self, data):
+        return data + torch.randn_like(data) * self.sigma

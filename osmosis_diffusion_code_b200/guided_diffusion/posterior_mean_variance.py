@@ -2,7 +2,8 @@
 
 Mirrors the registries of the reference `guided_diffusion/posterior_mean_variance.py` (:12-28, :143-159).
 In scope: model_mean_type `epsilon` (:104-136) and model_var_type
-`learned_range` (:227-258) - the pair every shipped osmosis config selects.  The other processor names of
+`learned_range` (:227-258) - the pair every shipped config selects - with optional `clip_denoised`
+(:41-50, rgb_guidance_sample_config.yaml).  The other processor names of
 the reference (`previous_x`, `start_x`, `fixed_small`, `fixed_large`, `learned`) are not registered here and
 raise NameError like any unknown name.
 
@@ -52,7 +53,7 @@ def get_var_processor(name: str, **kwargs):
 
 
 def coefficient_table(betas: np.ndarray) -> np.ndarray:
-    """[T, 8] fp32 rows {sqrt(1/abar), sqrt(1/abar - 1), coef1, coef2, log beta, clipped posterior log-var, 0, 0}."""
+    """[T, 8] fp32 rows {sqrt(1/abar), sqrt(1/abar - 1), coef1, coef2, log beta, clipped posterior log-var, abar, abar_prev}."""
     betas = np.asarray(betas, dtype=np.float64)
     alphas = 1.0 - betas
     ac = np.cumprod(alphas, axis=0)
@@ -65,6 +66,8 @@ def coefficient_table(betas: np.ndarray) -> np.ndarray:
     tab[:, 3] = (1.0 - acp) * np.sqrt(alphas) / (1.0 - ac)
     tab[:, 4] = np.log(betas)
     tab[:, 5] = np.log(np.append(post_var[1], post_var[1:])) if len(betas) > 1 else np.log(post_var)
+    tab[:, 6] = ac        # DDIM (gaussian_diffusion.py:512-513)
+    tab[:, 7] = acp
     return tab.astype(np.float32)
 
 
@@ -83,17 +86,19 @@ class _DeviceTable:
 
 
 class PosteriorFn(torch.autograd.Function):
-    """(x, model_out[B,2C,H,W]) -> (pred_xstart, mean, log_variance); differentiable in x and model_out."""
+    """(x, model_out[B,2C,H,W]) -> (pred_xstart, mean, log_variance); differentiable in x and model_out.
+    clip_denoised: pred_xstart clamped to [-1, 1] before the mean (process_xstart, reference :41-50)."""
 
     @staticmethod
-    def forward(ctx, x, model_out, coef, t_idx):
+    def forward(ctx, x, model_out, coef, t_idx, clip_denoised=False):
         B, Cc, H, W = x.shape
         x = x.contiguous(); model_out = model_out.contiguous()
         x0, mean, logvar = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
         L = _lib.load()
-        _lib.check(L.osm_posterior_fwd(_lib.ptr(coef), _lib.ptr(t_idx), _lib.ptr(x), _lib.ptr(model_out), _lib.ptr(x0),
-                                       _lib.ptr(mean), _lib.ptr(logvar), B, Cc, H * W, _lib.stream()))
+        _lib.check(L.osm_posterior_fwd_ex(_lib.ptr(coef), _lib.ptr(t_idx), _lib.ptr(x), _lib.ptr(model_out), _lib.ptr(x0),
+                                          _lib.ptr(mean), _lib.ptr(logvar), B, Cc, H * W, int(bool(clip_denoised)), _lib.stream()))
         ctx.coef, ctx.t_idx, ctx.shape = coef, t_idx, (B, Cc, H, W)
+        ctx.clip_inputs = (x.detach(), model_out.detach()) if clip_denoised else (None, None)
         return x0, mean, logvar
 
     @staticmethod
@@ -105,9 +110,11 @@ class PosteriorFn(torch.autograd.Function):
         c = lambda g: None if g is None else g.contiguous()
         g_x0, g_mean, g_logvar = c(g_x0), c(g_mean), c(g_logvar)
         L = _lib.load()
-        _lib.check(L.osm_posterior_vjp(_lib.ptr(ctx.coef), _lib.ptr(ctx.t_idx), _lib.ptr(g_x0), _lib.ptr(g_mean),
-                                       _lib.ptr(g_logvar), _lib.ptr(g_x), _lib.ptr(g_mo), B, Cc, H * W, _lib.stream()))
-        return g_x, g_mo, None, None
+        xc, moc = ctx.clip_inputs
+        _lib.check(L.osm_posterior_vjp_ex(_lib.ptr(ctx.coef), _lib.ptr(ctx.t_idx), _lib.ptr(g_x0), _lib.ptr(g_mean),
+                                          _lib.ptr(g_logvar), _lib.ptr(g_x), _lib.ptr(g_mo), B, Cc, H * W, _lib.ptr(xc),
+                                          _lib.ptr(moc), _lib.stream()))
+        return g_x, g_mo, None, None, None
 
 
 def _t_index(t):
@@ -119,14 +126,15 @@ class EpsilonXMeanProcessor:
     """x0 = sqrt(1/abar) x - sqrt(1/abar - 1) eps ; mean = coef1 x0 + coef2 x.   (reference :104-136)"""
 
     def __init__(self, betas, dynamic_threshold, clip_denoised):
-        if dynamic_threshold or clip_denoised:
-            raise NotImplementedError("dynamic_threshold / clip_denoised are not used by the osmosis configs")
+        if dynamic_threshold:
+            raise NotImplementedError("dynamic_threshold is not selected by any shipped config")
+        self.clip_denoised = bool(clip_denoised)
         self.table = _DeviceTable(betas)
 
     def get_mean_and_xstart(self, x, t, model_output):
         # stand-alone form: the variance half is not available here, feed zeros for it
         mo = torch.cat([model_output, torch.zeros_like(model_output)], dim=1)
-        x0, mean, _ = PosteriorFn.apply(x, mo, self.table.on(x.device), _t_index(t))
+        x0, mean, _ = PosteriorFn.apply(x, mo, self.table.on(x.device), _t_index(t), self.clip_denoised)
         return mean, x0
 
 

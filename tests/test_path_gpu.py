@@ -115,7 +115,7 @@ def test_sampler_update_and_uncond_update():
                                               L_.ptr(gout), B, Cc, H * W, L_.stream()))
             torch.cuda.synchronize()
             assert maxdiff(gout.cpu(), gsum) == 0.0
-            assert rel_err(out.cpu(), want) < 1e-6   # expf differs from the CPU exp by <= 2 ulp
+            assert rel_err(out.cpu(), want) < 3e-6   # expf vs the host's exp: a few ulp, and the host's vectorised exp varies by CPU
     x = torch.randn(1, 4, H, W, generator=g); mo = torch.randn(1, 8, H, W, generator=g); zz = torch.randn(1, 4, H, W, generator=g)
     a, ab, bt = 0.98, 0.3, 0.015
     want = orc.ddpm_uncond_update(x, mo[:, :4], zz, np.float64(a), np.float64(ab), np.float64(bt))
