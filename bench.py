@@ -153,11 +153,15 @@ def run_native(args):
     barrier()
     if clocks: clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:   # ncu --profile-from-start off: the launch list then holds the timed steps only
+        torch.cuda.profiler.start()
     e0.record()
     for idx in idxs[W:]:
         step(idx)
     e1.record()
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if clocks else None
     finite = bool(torch.isfinite(img).all())
@@ -346,6 +350,7 @@ def main():
     ap.add_argument("--config", default=os.path.join(ROOT, "configs", "osmosis_sample_config.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed device-resident region")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

@@ -285,3 +285,38 @@ def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
     scale = float(d.abs().mean())
     assert float((bst[:, :, 0].double() - m1).abs().max()) < 2e-4 * scale
     assert float((bst[:, :, 1].double() - m2).abs().max()) < 2e-4 * scale
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 256, 9), (1, 24, 40, 96, 512, 9), (3, 32, 32, 256, 256, 1), (1, 128, 128, 32, 256, 9)],
+                         ids=str)
+def test_conv_cta_pair_kernel(case, monkeypatch):
+    """conv_tc_persist_2sm_kernel (tcgen05.mma.cta_group::2, one 256-row MMA per CTA pair): forward, input gradient, residual
+    and `+=` epilogues against torch, forced on shapes with even / odd 128-pixel tile counts and partial tiles
+    (OSM_CONV_2SM=2 applies it wherever the plan is 256-wide and persistent; the default policy needs a full wave of pairs)."""
+    monkeypatch.setenv("OSM_CONV_2SM", "2")
+    monkeypatch.setenv("OSM_CONV_NO_SPLIT", "1")
+    B, H, W, cin, cout, taps = case
+    g = torch.Generator().manual_seed(sum(case))
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * taps)
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(B, cout, H, W, generator=g)
+    ref = F.conv2d(x, w, b, padding=k // 2)
+    wf, wd, cout_p, cin_p = pack_weight(w, taps, round_tf32=True)
+    xp = torch.zeros(B, H, W, cin_p, device=DEV); xp[..., :cin] = nhwc(x)
+    bp = torch.zeros(cout_p, device=DEV); bp[:cout] = b.to(DEV)
+    out = torch.full((B, H, W, cout_p), float("nan"), device=DEV)
+    run_conv(0, xp, cin_p, wf, bp, None, 0, 0, out, cout_p, 0, B, H, W, cin_p, cout_p, taps)
+    assert rel_err(nchw(out)[:, :cout], ref) < TF32_TOL
+    rp = nhwc(res)
+    run_conv(0, xp, cin_p, wf, bp, rp, cout, 1, out, cout_p, 0, B, H, W, cin_p, cout_p, taps)      # + residual
+    assert rel_err(nchw(out)[:, :cout], ref + res) < TF32_TOL
+    run_conv(0, xp, cin_p, wf, bp, None, 0, 0, out, cout_p, 1, B, H, W, cin_p, cout_p, taps)        # +=
+    assert rel_err(nchw(out)[:, :cout], 2 * ref + res) < TF32_TOL
+    gy = torch.randn(B, cout, H, W, generator=g)
+    gref = torch.autograd.grad(F.conv2d(x.requires_grad_(True), w, b, padding=k // 2), x, gy)[0]
+    gyp = torch.zeros(B, H, W, cout_p, device=DEV); gyp[..., :cout] = nhwc(gy)
+    gx = torch.full((B, H, W, cin_p), float("nan"), device=DEV)
+    run_conv(0, gyp, cout_p, wd, None, None, 0, 0, gx, cin_p, 0, B, H, W, cout_p, cin_p, taps)      # dgrad: Cin_p may be < 256
+    assert rel_err(nchw(gx)[:, :cin], gref) < TF32_TOL

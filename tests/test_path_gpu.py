@@ -385,3 +385,40 @@ def test_loop_reuse_and_host_measurement_progress():
     assert np.array_equal(seen1[-1][1], loss1)
     for (_, a), (_, b) in zip(seen1, seen2):
         assert np.array_equal(a, b)
+
+
+def test_simulation_batch_psnr_vs_oracle():
+    """BASELINE config 4 in miniature (osmosis_simulation_sample_config, a batch of distinct synthetic scenes, product mode =
+    tcgen05 TF32 convs + fused attention): PSNR of the restored RGB (pred_xstart[:, :3], data range 2.0) against the oracle's
+    fp32 chain with the same injected noise, per image, after the 6-step chain.  Also the per-image semantics of a batch: the
+    batched run equals the images run one by one to TF32 rounding."""
+    from osmosis_diffusion_code_b200.synthetic import synth_measurement
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    cname, B = "simulation", 3
+    cfg, op, cond, sampler = _native_objects(cname, B)
+    tab, ospec, gspec, phis, names = oracle_specs_from_cfg(cfg, B)
+    ys = torch.cat([synth_measurement(10 + i, 32, phi_a=(1.1, 0.95, 0.95), phi_b=(1.1, 0.95, 0.95), phi_inf=(0.2, 0.4, 0.7),
+                                      depth_type="original")[0] for i in range(B)], 0)
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(1, 4, 32, 32, generator=g).repeat(B, 1, 1, 1)           # the reference reseeds per image: shared x_T / noise
+    noises = {idx: torch.randn(1, 4, 32, 32, generator=g).repeat(B, 1, 1, 1) for idx in range(tab.num_timesteps)}
+    xo, pho, losso, x0o = orc.sample_loop(small_state_dict(), small_cfg(), tab, ospec, gspec, x_T, ys, phis, lambda i: noises[i])
+
+    def run(model_, cond_, sampler_, y_, x_, nz):
+        img = x_.to(DEV).clone()
+        stepper = FusedStepper(sampler_, model_, cond_, img, y_.to(DEV), cfg["sample_pattern"], cuda_graph=True)
+        for idx in range(sampler_.num_timesteps)[::-1]:
+            stepper._draw_into = lambda buf, _i=idx: buf.copy_(nz[_i].to(DEV)) if buf.shape[1] == 4 else buf.zero_()
+            stepper.step(idx)
+        torch.cuda.synchronize()
+        return stepper.st["x0"].cpu()
+
+    x0 = run(model("tc"), cond, sampler, ys, x_T, noises)
+    mse = ((x0[:, :3] - x0o[:, :3]) ** 2).mean(dim=(1, 2, 3))
+    psnr = 10 * torch.log10(4.0 / mse)
+    assert float(psnr.min()) > 40.0, psnr          # measured 50-60 dB: TF32 rounding + rare clamp sign flips over 6 steps
+    for b in range(B):
+        _, op1, cond1, sampler1 = _native_objects(cname, 1)
+        x0_1 = run(model("tc"), cond1, sampler1, ys[b:b + 1], x_T[b:b + 1], {k: v[b:b + 1] for k, v in noises.items()})
+        m1 = ((x0_1[:, :3] - x0[b:b + 1, :3]) ** 2).mean()
+        assert float(10 * torch.log10(4.0 / m1.clamp_min(1e-20))) > 40.0
