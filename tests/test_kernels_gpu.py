@@ -164,7 +164,11 @@ def _gn_ref(x, gamma, beta, ss, silu, resample):
 
 
 @pytest.mark.parametrize("case", GN_CASES, ids=[str(c) for c in GN_CASES])
-def test_groupnorm_forward_backward(case):
+@pytest.mark.parametrize("small", ["1", "0"], ids=["one-launch", "two-kernel"])
+def test_groupnorm_forward_backward(case, small, monkeypatch):
+    # OSM_GN_SMALL: eligible tensors (no resample, <= 32768 elements per group) run statistics + apply in one launch
+    # (gn_small_*_kernel); "0" forces the stats / apply kernel pair so both paths stay covered on every shape
+    monkeypatch.setenv("OSM_GN_SMALL", small)
     B, H, W, Cc, silu, mod, rs = case
     g = torch.Generator().manual_seed(11 + Cc + H)
     x = (torch.randn(B, Cc, H, W, generator=g) * 1.7 + 0.6).requires_grad_(True)
