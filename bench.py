@@ -220,7 +220,7 @@ def run_native(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     tf32 = measure_tf32_peak(dev)
-    roofline = dict(bound="tensor", kernel="conv_tc_persist_kernel<256,4> (3x3 256->256 @256x256 implicit GEMM, fwd + dgrad launches)",
+    roofline = dict(bound="tensor", kernel="conv_tc_persist_2sm_kernel<6,.> (3x3 256->256 @256x256 tcgen05 cta_group::2 TF32 implicit GEMM, fwd + dgrad launches)",
                     achieved=round(dom_tf, 1), peak=peaks["bf16_sustained"], unit="TFLOP/s",
                     frac=round(dom_tf / peaks["bf16_sustained"], 4), traffic=traffic,
                     peak_source=f"{peaks['source']} bf16 sustained from MEASURED_PEAKS.json (kernel timed inside the step)",

@@ -8,7 +8,7 @@ timeout 600 python bench.py --batch 8 --no-cpu-baseline --steps 30 --warmup 3 > 
 timeout 600 python bench.py --batch 32 --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/bench_b32.json 2> gpurun_out/bench_b32.err; head -c 300 gpurun_out/bench_b32.json; echo
 timeout 400 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; head -c 300 gpurun_out/bench_ref.json; echo
 for b in 1 8; do timeout 300 python tools/profile_step.py --batch $b > gpurun_out/step_b$b.log 2>&1; done
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph > gpurun_out/launches_bench.log 2>&1
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-cuda-graph --profiler-range > gpurun_out/launches_bench.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.md
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -o gpurun_out/r01_conv_final python tools/ncu_conv.py 1,256,256,256,256,9 8,256,256,256,256,9 1,8,8,1024,1024,9 > gpurun_out/ncu_conv.log 2>&1
 python tools/ncu_summary.py gpurun_out/r01_conv_final.ncu-rep > gpurun_out/ncu_conv_summary.md
