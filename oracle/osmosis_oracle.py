@@ -638,6 +638,33 @@ def ddpm_uncond_update(x, eps, z, alpha_t, alphabar_t, beta_tilde):
     return (1 / np.sqrt(alpha_t)) * (x - ((1 - alpha_t) / np.sqrt(1 - alphabar_t)) * eps) + np.sqrt(beta_tilde) * z
 
 
+def uncond_inverse(sd, cfg: UNetConfig, T: int, schedule: str, x_T: torch.Tensor, z_fn, start_t=None, steps=None,
+                   image_channels: int = 4):
+    """osmosis_utils/diffusion.py:59-130 (`GaussianDiffusion.inverse`, BASELINE config 1): unguided ancestral sampling with
+    the fixed-small variance, 1-indexed float timesteps, an un-rescaled linear schedule and a truncated (not respaced) chain.
+    z_fn(t) -> noise [B,C,H,W] for t > 1.  Returns (x, pred_xstart at the last step)."""
+    if schedule != "linear":
+        raise NotImplementedError
+    beta = np.linspace(1e-4, 2e-2, T)
+    alpha = 1 - beta
+    alphabar = np.cumprod(alpha)
+    start_t = T if start_t is None else start_t
+    steps = T if steps is None else steps
+    x, x0 = x_T, None
+    for t in range(start_t, start_t - steps, -1):
+        at, atbar = alpha[t - 1], alphabar[t - 1]
+        if t > 1:
+            z = z_fn(t)
+            beta_tilde = beta[t - 1] * (1 - alphabar[t - 2]) / (1 - atbar)
+        else:
+            z, beta_tilde = torch.zeros_like(x), 0
+        with torch.no_grad():
+            pred = unet_forward(sd, cfg, x, torch.tensor([float(t)] * x.shape[0]))[:, :image_channels]
+        x0 = (1 / np.sqrt(atbar)) * (x - (np.sqrt(1 - atbar) * pred))
+        x = (1 / np.sqrt(at)) * (x - ((1 - at) / np.sqrt(1 - atbar)) * pred) + np.sqrt(beta_tilde) * z
+    return x, x0
+
+
 # --------------------------------------------------------------------------------------
 # YAML -> oracle specs (measurements.py:108-136, 212-249, 333-361; condition_methods.py:63-107)
 # --------------------------------------------------------------------------------------

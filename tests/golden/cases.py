@@ -106,3 +106,7 @@ def ps_measurement():
     g = _gen("ps:meas")
     low = torch.rand(1, 3, 4, 4, generator=g)
     return (2 * torch.nn.functional.interpolate(low, size=SMALL_HW, mode="bilinear", align_corners=False) - 1).contiguous()
+
+
+# BASELINE config 1 (unguided RGBD prior sampling, osmosis_utils/diffusion.py): last 6 steps of a T = 50 chain
+UNCOND_CASE = dict(T=50, start_t=6, steps=6, seed=4321)

@@ -422,3 +422,30 @@ def test_simulation_batch_psnr_vs_oracle():
         x0_1 = run(model("tc"), cond1, sampler1, ys[b:b + 1], x_T[b:b + 1], {k: v[b:b + 1] for k, v in noises.items()})
         m1 = ((x0_1[:, :3] - x0[b:b + 1, :3]) ** 2).mean()
         assert float(10 * torch.log10(4.0 / m1.clamp_min(1e-20))) > 40.0
+
+
+def test_uncond_inverse_vs_reference_golden(tmp_path, monkeypatch):
+    """BASELINE config 1 (`RGBD_prior_sampling.py`): `osmosis_utils.diffusion.GaussianDiffusion.inverse` with the native UNet and
+    the osm_ddpm_uncond_update kernel against the unmodified reference's run (CPU RNG draws injected), including the recorded
+    x_start_rgb / depth outputs and the process grid file."""
+    import os
+    from osmosis_diffusion_code_b200.osmosis_utils.diffusion import GaussianDiffusion
+    from osmosis_diffusion_code_b200.osmosis_utils import utils as utilso
+    from tests.golden.cases import UNCOND_CASE, SMALL_HW
+    gold = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "uncond_golden.npz")))
+    c = UNCOND_CASE
+    torch.manual_seed(c["seed"])
+    x_T = torch.randn(1, 4, SMALL_HW, SMALL_HW)
+    zs = [torch.randn(1, 4, SMALL_HW, SMALL_HW) for _ in range(c["steps"] - 1)]
+    it = iter(zs)
+    monkeypatch.setattr(torch, "randn_like", lambda t, **kw: next(it).to(t.device))
+    monkeypatch.setattr(utilso, "depth_tensor_to_color_image", lambda d, **kw: d.repeat(3, 1, 1) if d.dim() == 3 else d)  # identity map
+    m = model("fp32")
+    x, (rgb, depth) = GaussianDiffusion(T=c["T"], schedule="linear").inverse(
+        net=m, shape=(4, SMALL_HW, SMALL_HW), image_channels=4, steps=c["steps"], start_t=c["start_t"], device=DEV, x=x_T.to(DEV),
+        record_process=True, record_every=200, save_path=str(tmp_path), image_idx=0)
+    torch.cuda.synchronize()
+    assert maxdiff(x.cpu(), gold["x"]) < 1e-4 * max(1.0, float(np.abs(gold["x"]).max()))
+    assert maxdiff(rgb.cpu(), gold["x_start_rgb"]) < 1e-4
+    assert maxdiff(depth[0:1].cpu(), gold["x_depth_pmm"]) < 5e-4
+    assert os.path.exists(os.path.join(str(tmp_path), "image_0_process.png"))
