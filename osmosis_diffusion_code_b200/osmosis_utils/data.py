@@ -138,8 +138,9 @@ class ShardedImageLoader:
     independent, so no collective is involved.  `extras` holds the ground-truth tensors for a GT dataset."""
 
     def __init__(self, dataset, batch_per_rank: int, rank: int = 0, world: int = 1, device=None, degamma: bool = False,
-                 stop_after: int = -1):
+                 stop_after: int = -1, size: int = IMAGE_SIZE):
         self.ds, self.b, self.rank, self.world, self.device, self.degamma = dataset, batch_per_rank, rank, world, device, degamma
+        self.size = size
         n = len(dataset) if stop_after is None or stop_after < 0 else min(len(dataset), stop_after)
         self.indices = list(range(rank, n, world))
 
@@ -151,9 +152,9 @@ class ShardedImageLoader:
             items = [self.ds[i] for i in self.indices[s:s + self.b]]
             names = [n for _, n in items]
             if isinstance(items[0][0], (list, tuple)):
-                y = preprocess_batch([it[0][0] for it in items], self.device, degamma=self.degamma)
-                gt_rgb = preprocess_batch([it[0][1] for it in items], self.device)
-                gt_depth = preprocess_batch([it[0][2] for it in items], self.device)
+                y = preprocess_batch([it[0][0] for it in items], self.device, size=self.size, degamma=self.degamma)
+                gt_rgb = preprocess_batch([it[0][1] for it in items], self.device, size=self.size)
+                gt_depth = preprocess_batch([it[0][2] for it in items], self.device, size=self.size)
                 yield y, names, dict(gt_rgb=gt_rgb, gt_depth=gt_depth)
             else:
-                yield preprocess_batch([it[0] for it in items], self.device, degamma=self.degamma), names, {}
+                yield preprocess_batch([it[0] for it in items], self.device, size=self.size, degamma=self.degamma), names, {}
