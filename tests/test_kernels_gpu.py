@@ -291,13 +291,16 @@ def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
     assert float((bst[:, :, 1].double() - m2).abs().max()) < 2e-4 * scale
 
 
-@pytest.mark.parametrize("case", [(2, 64, 64, 64, 256, 9), (1, 24, 40, 96, 512, 9), (3, 32, 32, 256, 256, 1), (1, 128, 128, 32, 256, 9)],
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 256, 9), (1, 24, 40, 96, 512, 9), (3, 32, 32, 256, 256, 1), (1, 128, 128, 32, 256, 9),
+                                  # stream-K: tiles shared between consecutive CTA pairs (partial sums through the workspace)
+                                  (2, 64, 64, 256, 256, 9), (1, 96, 96, 128, 512, 9), (1, 128, 128, 256, 256, 9), (1, 72, 88, 192, 256, 9)],
                          ids=str)
 def test_conv_cta_pair_kernel(case, monkeypatch):
     """conv_tc_persist_2sm_kernel (tcgen05.mma.cta_group::2, one 256-row MMA per CTA pair): forward, input gradient, residual
     and `+=` epilogues against torch, forced on shapes with even / odd 128-pixel tile counts and partial tiles
     (OSM_CONV_2SM=2 applies it wherever the plan is 256-wide and persistent; the default policy needs a full wave of pairs)."""
     monkeypatch.setenv("OSM_CONV_2SM", "2")
+    monkeypatch.setenv("OSM_CONV_SK", "2")
     monkeypatch.setenv("OSM_CONV_NO_SPLIT", "1")
     B, H, W, cin, cout, taps = case
     g = torch.Generator().manual_seed(sum(case))
