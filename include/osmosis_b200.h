@@ -87,8 +87,9 @@ int osm_unet_profile_ops(osm_unet_t h, int which, void* stream, int cap, float* 
                          double* bytes, int* dims6);
 
 /* ------------------------------------------------------------- sampler elementwise ---------------------
- * coef: [T][8] fp32 rows = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
- * posterior_mean_coef2, log(beta), posterior_log_variance_clipped, alphas_cumprod, alphas_cumprod_prev}, each the fp32 rounding of the
+ * coef: [T][OSM_COEF_COLS] fp32 rows = {sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1,
+ * posterior_mean_coef2, log(beta), posterior_log_variance_clipped, alphas_cumprod, alphas_cumprod_prev,
+ * log(posterior_variance), log(append(posterior_variance[1], betas[1:])), 1 / coef1, coef2 / coef1}, each the fp32 rounding of the
  * reference's float64 table entry (posterior_mean_variance.py:265-269).  t_idx[B]: int32 respaced index. */
 
 /* replaces EpsilonXMeanProcessor.get_mean_and_xstart (posterior_mean_variance.py:104-136) and
@@ -100,14 +101,27 @@ int osm_posterior_fwd(const float* coef, const int32_t* t_idx, const float* x, c
  * g_x [B,C,HW] (direct path through x), g_model_out [B,2C,HW].                                        */
 int osm_posterior_vjp(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean,
                       const float* g_logvar, float* g_x, float* g_model_out, int B, int C, int HW, void* stream);
-/* The same two with `clip_denoised` (MeanProcessor.process_xstart, posterior_mean_variance.py:41-50): x0 is clamped to
- * [-1, 1] before the posterior mean; the VJP recomputes the unclamped x0 from x / model_out (both NULL = no clamp) and
- * passes the gradient only where it lay inside [-1, 1], as torch's clamp backward does.                            */
+/* The same two for every mean / variance processor of the reference's registries and `clip_denoised`
+ * (posterior_mean_variance.py:41-50 process_xstart, :54-136 mean processors, :173-258 variance processors).
+ * flags = OSM_POST_CLIP | OSM_POST_MEAN_* | OSM_POST_VAR_*  (0 = epsilon + learned_range, no clamp).  With the clamp, x0 is
+ * clamped to [-1, 1] before the posterior mean; the VJP recomputes the unclamped x0 from x / model_out and passes the
+ * gradient only where it lay inside [-1, 1], as torch's clamp backward does.                                        */
+#define OSM_COEF_COLS 12
+#define OSM_POST_CLIP 0x1
+#define OSM_POST_MEAN_MASK 0xF0
+#define OSM_POST_MEAN_EPSILON 0x00   /* :104-136 */
+#define OSM_POST_MEAN_STARTX 0x10    /* :76-101  x0 = model_out                          */
+#define OSM_POST_MEAN_PREVX 0x20     /* :54-73   mean = model_out, x0 = mean / coef1 - coef2 / coef1 x */
+#define OSM_POST_VAR_MASK 0xF00
+#define OSM_POST_VAR_LEARNED_RANGE 0x000 /* :227-258 */
+#define OSM_POST_VAR_LEARNED 0x100       /* :217-224 log variance = model_out[:, C:]     */
+#define OSM_POST_VAR_FIXED_SMALL 0x200   /* :173-191 log(posterior_variance)             */
+#define OSM_POST_VAR_FIXED_LARGE 0x300   /* :194-214 log(append(posterior_variance[1], betas[1:])) */
 int osm_posterior_fwd_ex(const float* coef, const int32_t* t_idx, const float* x, const float* model_out, float* x0,
-                         float* mean, float* logvar, int B, int C, int HW, int clip_denoised, void* stream);
+                         float* mean, float* logvar, int B, int C, int HW, int flags, void* stream);
 int osm_posterior_vjp_ex(const float* coef, const int32_t* t_idx, const float* g_x0, const float* g_mean,
                          const float* g_logvar, float* g_x, float* g_model_out, int B, int C, int HW, const float* x,
-                         const float* model_out, void* stream);
+                         const float* model_out, int flags, void* stream);
 /* replaces condition_methods.py:211-223 + gaussian_diffusion.py:266-271:
  *   x_out = mean - scale[c] * clamp(g_a + g_b, +-clip) + [t_idx != 0] * exp(0.5*logvar) * noise
  * g_b may be NULL; clip < 0 disables clamping.  The clamped-before-scale raw gradient g_a+g_b is written to

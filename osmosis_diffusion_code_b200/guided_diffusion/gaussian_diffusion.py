@@ -128,6 +128,11 @@ class GaussianDiffusion:
                                                  clip_denoised=clip_denoised)
         self.var_processor = get_var_processor(model_var_type, betas=betas)
 
+    @property
+    def posterior_flags(self):
+        """OSM_POST_* flags of this sampler's mean / variance processors and clip_denoised (include/osmosis_b200.h)."""
+        return self.mean_processor.flags | self.var_processor.flags
+
     # ---- pieces of the reference API --------------------------------------------------------------------
     def q_sample(self, x_start, t):
         """sqrt(abar_t) x + sqrt(1 - abar_t) randn - the osmosis path only needs its RNG side effect (:241)."""
@@ -146,8 +151,7 @@ class GaussianDiffusion:
         if model_output.shape[1] != 2 * x.shape[1]:
             raise NotImplementedError("the native posterior kernel expects a learned-variance model (2C output channels)")
         coef = self.mean_processor.table.on(x.device)
-        x0, mean, logvar = PosteriorFn.apply(x, model_output, coef, t.to(torch.int32).contiguous(),
-                                             self.mean_processor.clip_denoised)
+        x0, mean, logvar = PosteriorFn.apply(x, model_output, coef, t.to(torch.int32).contiguous(), self.posterior_flags)
         return {"mean": mean, "variance": torch.exp(logvar.detach()), "log_variance": logvar, "pred_xstart": x0}
 
     def p_sample(self, model, x, t):
@@ -225,12 +229,15 @@ class GaussianDiffusion:
         B, Cc, H, W = img.shape
         HW = H * W
         s = _lib.stream()
+        flags = self.posterior_flags
+        clip = bool(flags & 1)
         model._forward_raw(img, st["t_model"], out=st["model_out"])
-        _lib.check(L.osm_posterior_fwd(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
-                                       _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, s))
+        _lib.check(L.osm_posterior_fwd_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
+                                          _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, flags, s))
         cond.guidance_gradient(st["x0"], st["y"], st["freeze"], st["g_x0"], st["losses"])
-        _lib.check(L.osm_posterior_vjp(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(st["g_x0"]), None, None,
-                                       _lib.ptr(st["g_direct"]), _lib.ptr(st["g_mo"]), B, Cc, HW, s))
+        _lib.check(L.osm_posterior_vjp_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(st["g_x0"]), None, None,
+                                          _lib.ptr(st["g_direct"]), _lib.ptr(st["g_mo"]), B, Cc, HW,
+                                          _lib.ptr(img) if clip else None, _lib.ptr(st["model_out"]) if clip else None, flags, s))
         model._vjp_raw(st["g_mo"], grad_x=st["g_unet"])
         _lib.check(L.osm_sampler_update(_lib.ptr(st["mean"]), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
                                         _lib.ptr(st["scale"]), st["clip"], _lib.ptr(st["logvar"]), _lib.ptr(noise),
@@ -245,8 +252,9 @@ class GaussianDiffusion:
         HW = H * W
         s = _lib.stream()
         model._forward_raw(img, st["t_model"], out=st["model_out"])
-        _lib.check(L.osm_posterior_fwd(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
-                                       _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, s))
+        _lib.check(L.osm_posterior_fwd_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
+                                          _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW,
+                                          self.posterior_flags, s))
         _lib.check(L.osm_sampler_update(_lib.ptr(st["mean"]), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
                                         _lib.ptr(st["zero_scale"]), -1.0, _lib.ptr(st["logvar"]), _lib.ptr(noise),
                                         _lib.ptr(st["t_idx"]), _lib.ptr(img), None, B, Cc, HW, s))
@@ -261,10 +269,11 @@ class GaussianDiffusion:
         B, Cc, H, W = img.shape
         HW = H * W
         s = _lib.stream()
-        clip = int(self.mean_processor.clip_denoised)
+        flags = self.posterior_flags
+        clip = flags & 1
         model._forward_raw(img, st["t_model"], out=st["model_out"])
         _lib.check(L.osm_posterior_fwd_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["model_out"]),
-                                          _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, clip, s))
+                                          _lib.ptr(st["x0"]), _lib.ptr(st["mean"]), _lib.ptr(st["logvar"]), B, Cc, HW, flags, s))
         base, t_noise = st["mean"], st["t_idx"]
         if self.ddim_eta is not None:   # the DDIM sample replaces mean + sigma z; the update kernel then adds no noise
             _lib.check(L.osm_ddim_sample(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(img), _lib.ptr(st["x0"]),
@@ -273,7 +282,7 @@ class GaussianDiffusion:
         cond.guidance_gradient(st["x0"], st["y"], st["g_x0"], st["ps_loss"])
         _lib.check(L.osm_posterior_vjp_ex(_lib.ptr(st["coef"]), _lib.ptr(st["t_idx"]), _lib.ptr(st["g_x0"]), None, None,
                                           _lib.ptr(st["g_direct"]), _lib.ptr(st["g_mo"]), B, Cc, HW,
-                                          _lib.ptr(img) if clip else None, _lib.ptr(st["model_out"]) if clip else None, s))
+                                          _lib.ptr(img) if clip else None, _lib.ptr(st["model_out"]) if clip else None, flags, s))
         model._vjp_raw(st["g_mo"], grad_x=st["g_unet"])
         _lib.check(L.osm_sampler_update_ex(_lib.ptr(base), _lib.ptr(st["g_direct"]), _lib.ptr(st["g_unet"]),
                                            _lib.ptr(st["scale"]), -1.0, _lib.ptr(st["logvar"]), _lib.ptr(noise),

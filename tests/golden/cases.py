@@ -110,3 +110,15 @@ def ps_measurement():
 
 # BASELINE config 1 (unguided RGBD prior sampling, osmosis_utils/diffusion.py): last 6 steps of a T = 50 chain
 UNCOND_CASE = dict(T=50, start_t=6, steps=6, seed=4321)
+
+
+# (mean processor, variance processor, clip_denoised) combinations of the reference's registries
+PROC_CASES = [("epsilon", "learned_range", True), ("start_x", "fixed_small", True), ("start_x", "learned", False),
+              ("previous_x", "fixed_large", True), ("previous_x", "learned_range", False), ("epsilon", "fixed_small", False)]
+
+
+def proc_inputs():
+    g = _gen("proc")
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    mo = 0.8 * x.repeat(1, 2, 1, 1) + 0.5 * torch.randn(2, 8, 16, 16, generator=g)
+    return x, mo

@@ -96,6 +96,22 @@ def main():
         for k, v in vd.items():
             out[f"mse/step{idx}/{k}"] = v.detach().numpy()
         print("mse", idx, "freeze", freeze, loss)
+    # ---------------------------------------------------------------- every mean / variance processor of the registries
+    from guided_diffusion.posterior_mean_variance import get_mean_processor, get_var_processor
+    from tests.golden.cases import PROC_CASES, proc_inputs
+    d = dict(cfg["diffusion"]); d["timestep_respacing"] = 6
+    betas = create_sampler(**d).betas
+    x, mo = proc_inputs()
+    for mean_type, var_type, clip in PROC_CASES:
+        mp = get_mean_processor(mean_type, betas=betas, dynamic_threshold=False, clip_denoised=clip)
+        vp = get_var_processor(var_type, betas=betas)
+        for idx in (0, 3, 5):
+            t = torch.tensor([idx] * x.shape[0])
+            mean, x0 = mp.get_mean_and_xstart(x, t, mo[:, :4])
+            var, logvar = vp.get_variance(mo[:, 4:], t)
+            key = f"proc/{mean_type}/{var_type}/{int(clip)}/{idx}/"
+            out[key + "mean"], out[key + "x0"] = mean.numpy(), x0.numpy()
+            out[key + "logvar"] = np.broadcast_to(logvar.numpy(), x.shape).astype(np.float32).copy()
     np.savez_compressed(os.path.join(HERE, "ps_golden.npz"), **out)
     print("wrote", len(out), "arrays")
 

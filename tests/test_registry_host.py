@@ -25,7 +25,8 @@ def test_guided_configs_build(name):
     tab = orc.make_tables(a.diffusion["steps"], a.diffusion["noise_schedule"], a.diffusion["timestep_respacing"])
     assert np.array_equal(s.betas, tab.betas) and list(s.timestep_map) == list(tab.timestep_map)
     ct = coefficient_table(s.betas)
-    assert ct.shape == (s.num_timesteps, 8) and ct[5, 6] == np.float32(tab.alphas_cumprod[5]) and ct[0, 7] == 1.0
+    assert ct.shape == (s.num_timesteps, 12) and ct[5, 6] == np.float32(tab.alphas_cumprod[5]) and ct[0, 7] == 1.0
+    assert np.isneginf(ct[0, 8]) and ct[0, 10] == 1.0 and ct[7, 9] == np.float32(np.log(s.betas[7]))
     cond_cls = get_conditioning_method.__globals__["__CONDITIONING_METHOD__"][a.conditioning["method"]]
     assert cond_cls.__name__ == "PosteriorSamplingOsmosis"
     assert get_noise(**a.measurement["noise"]).__name__ == a.measurement["noise"]["name"]
@@ -44,9 +45,13 @@ def test_rgb_guidance_config_builds_without_a_device():
 
 
 def test_unknown_names_raise_like_the_reference():
-    for fn, arg in ((get_sampler, "plms"), (get_mean_processor, "previous_x"), (get_var_processor, "fixed_small")):
+    for fn, arg in ((get_sampler, "plms"), (get_mean_processor, "velocity"), (get_var_processor, "fixed_tiny")):
         with pytest.raises(NameError):
             fn(arg)
+    b = np.linspace(1e-4, 0.02, 10)
+    for name in ("epsilon", "start_x", "previous_x"):
+        assert get_mean_processor(name, betas=b, dynamic_threshold=False, clip_denoised=True).flags & 1
+    assert [get_var_processor(n, betas=b).flags for n in ("learned_range", "learned", "fixed_small", "fixed_large")] == [0, 0x100, 0x200, 0x300]
     with pytest.raises(NameError):
         get_operator("super_resolution", device="cpu")
     with pytest.raises(NameError):

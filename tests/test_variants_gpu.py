@@ -23,31 +23,43 @@ pytestmark = pytest.mark.gpu
 GOLD = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ps_golden.npz")))
 
 
+@pytest.mark.parametrize("mean_type,var_type,clip", [("epsilon", "learned_range", True), ("start_x", "fixed_small", True),
+                                                     ("start_x", "learned", False), ("previous_x", "fixed_large", True),
+                                                     ("previous_x", "learned_range", False), ("epsilon", "fixed_small", False)])
 @pytest.mark.parametrize("idx", [0, 3, 999])
-def test_posterior_clip_denoised_forward_and_vjp(idx):
+def test_posterior_processors_forward_and_vjp(idx, mean_type, var_type, clip):
+    """osm_posterior_fwd_ex / _vjp_ex for every mean / variance processor of the reference's registries and clip_denoised,
+    against the oracle (pinned to the reference's processor classes) and its autograd gradient."""
+    from osmosis_diffusion_code_b200.guided_diffusion.posterior_mean_variance import MEAN_KIND, VAR_KIND, POST_CLIP
     tab = orc.make_tables(1000, "linear", 1000)
     g = torch.Generator().manual_seed(idx + 7)
     B, Cc, H, W = 2, 4, 32, 32
     x = torch.randn(B, Cc, H, W, generator=g).requires_grad_(True)
     mo = (0.9 * x.detach() + 0.3 * torch.randn(B, 2 * Cc, H, W, generator=g)[:, :Cc]).repeat(1, 2, 1, 1).requires_grad_(True)
-    x0, mean, logvar = orc.posterior(tab, idx, x, mo, clip_denoised=True)
-    frac_clipped = float((x0.detach().abs() == 1).float().mean())
-    assert 0.005 < frac_clipped < 0.995 or idx == 0         # both sides of the clamp are exercised
+    x0, mean, logvar = orc.posterior(tab, idx, x, mo, clip_denoised=clip, mean_type=mean_type, var_type=var_type)
+    flags = MEAN_KIND[mean_type] | VAR_KIND[var_type] | (POST_CLIP if clip else 0)
     coef = torch.from_numpy(coefficient_table(tab.betas)).to(DEV)
     t_idx = torch.full((B,), idx, dtype=torch.int32, device=DEV)
     o = [torch.empty(B, Cc, H, W, device=DEV) for _ in range(3)]
     xd, mod = x.detach().to(DEV), mo.detach().to(DEV)
     lib = L_.load()
     L_.check(lib.osm_posterior_fwd_ex(L_.ptr(coef), L_.ptr(t_idx), L_.ptr(xd), L_.ptr(mod), L_.ptr(o[0]), L_.ptr(o[1]), L_.ptr(o[2]),
-                                      B, Cc, H * W, 1, L_.stream()))
+                                      B, Cc, H * W, flags, L_.stream()))
     torch.cuda.synchronize()
-    assert maxdiff(o[0].cpu(), x0.detach()) == 0.0 and maxdiff(o[1].cpu(), mean.detach()) == 0.0
-    g0, gm = (torch.randn(B, Cc, H, W, generator=g) for _ in range(2))
-    gx_ref, gmo_ref = torch.autograd.grad([x0, mean], [x, mo], [g0, gm])
+    assert maxdiff(o[0].cpu(), x0.detach()) == 0.0 and maxdiff(o[1].cpu(), mean.detach()) == 0.0      # op-by-op rounding mirrored
+    lv, want = o[2].cpu(), logvar.detach()
+    fin = torch.isfinite(want)
+    assert torch.equal(torch.isinf(lv), torch.isinf(want)) and (not bool(fin.any()) or maxdiff(lv[fin], want[fin]) == 0.0)
+    g0, gm, gl = (torch.randn(B, Cc, H, W, generator=g) for _ in range(3))
+    outs, cots = [x0, mean], [g0, gm]
+    if var_type in ("learned_range", "learned"):
+        outs.append(logvar); cots.append(gl)
+    gx_ref, gmo_ref = torch.autograd.grad(outs, [x, mo], cots, allow_unused=True)
+    gx_ref = torch.zeros_like(x) if gx_ref is None else gx_ref
     gx = torch.empty(B, Cc, H, W, device=DEV); gmo = torch.empty(B, 2 * Cc, H, W, device=DEV)
-    g0d, gmd = g0.to(DEV), gm.to(DEV)
-    L_.check(lib.osm_posterior_vjp_ex(L_.ptr(coef), L_.ptr(t_idx), L_.ptr(g0d), L_.ptr(gmd), None, L_.ptr(gx), L_.ptr(gmo), B, Cc,
-                                      H * W, L_.ptr(xd), L_.ptr(mod), L_.stream()))
+    g0d, gmd, gld = g0.to(DEV), gm.to(DEV), gl.to(DEV)
+    L_.check(lib.osm_posterior_vjp_ex(L_.ptr(coef), L_.ptr(t_idx), L_.ptr(g0d), L_.ptr(gmd), L_.ptr(gld), L_.ptr(gx), L_.ptr(gmo), B, Cc,
+                                      H * W, L_.ptr(xd) if clip else None, L_.ptr(mod) if clip else None, flags, L_.stream()))
     torch.cuda.synchronize()
     assert rel_err(gx.cpu(), gx_ref) < 2e-6 and rel_err(gmo.cpu(), gmo_ref) < 2e-6
 

@@ -73,3 +73,23 @@ def test_mse_loss_single_steps():
         assert maxdiff(x_t, GOLD[pre + "x_t"]) < 2e-5 * max(1.0, float(np.abs(GOLD[pre + "x_t"]).max()))
         for n, p in zip(names, r["phis"]):
             assert maxdiff(p, GOLD[pre + n]) < 2e-6
+
+
+def test_every_mean_and_variance_processor_matches_the_reference_registries():
+    """oracle.posterior(mean_type, var_type, clip_denoised) against the reference's own processor classes
+    (get_mean_processor / get_var_processor) on seeded inputs, three timesteps (t = 0 gives log(0) = -inf for fixed_small)."""
+    from tests.golden.cases import PROC_CASES, proc_inputs
+    cfg = load_yaml_cfg(PS_CASE["yaml"], 6)
+    d = cfg["diffusion"]
+    tab = orc.make_tables(d["steps"], d["noise_schedule"], 6)
+    x, mo = proc_inputs()
+    for mean_type, var_type, clip in PROC_CASES:
+        for idx in (0, 3, 5):
+            x0, mean, logvar = orc.posterior(tab, idx, x, mo, clip_denoised=clip, mean_type=mean_type, var_type=var_type)
+            key = f"proc/{mean_type}/{var_type}/{int(clip)}/{idx}/"
+            assert maxdiff(x0, GOLD[key + "x0"]) <= 1e-6 * max(1.0, float(np.abs(GOLD[key + "x0"]).max())), key
+            assert maxdiff(mean, GOLD[key + "mean"]) <= 1e-6 * max(1.0, float(np.abs(GOLD[key + "mean"]).max())), key
+            lv, want = logvar.numpy(), GOLD[key + "logvar"]
+            assert np.array_equal(np.isinf(lv), np.isinf(want)), key
+            fin = np.isfinite(want)
+            assert float(np.abs(lv[fin] - want[fin]).max(initial=0.0)) <= 1e-6 * max(1.0, float(np.abs(want[fin]).max(initial=0.0))), key
