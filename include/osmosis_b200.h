@@ -156,6 +156,8 @@ int osm_ddpm_uncond_update(float* x, const float* model_out, const float* z, flo
 #define OSM_DEPTH_GAMMA 1           /* utils.py:557-558  ((d+v0)*v1)^v2                                 */
 #define OSM_DEPTH_MOVE 2            /* utils.py:554-555  d+v0                                           */
 
+#define OSM_OPT_SGD 0
+#define OSM_OPT_ADAM 1
 #define OSM_LOSS_NORM 0             /* condition_methods.py:127-130  ||r||_2                            */
 #define OSM_LOSS_MSE 1              /* condition_methods.py:133-138  mean(r^2) per image                */
 
@@ -171,6 +173,10 @@ typedef struct osm_guidance_params {
   float gamma_avrg;      /* aux_loss.avrg_loss weight, 0 if absent (losses.py:29-45)                    */
   float gamma_val;       /* aux_loss.val_loss weight, 0 if absent  (losses.py:51-62)                    */
   int loss_kind;         /* OSM_LOSS_NORM / OSM_LOSS_MSE: loss_function (condition_methods.py:127-138)  */
+  int optimizer;         /* OSM_OPT_SGD (sgd / GD, measurements.py:279-303) or OSM_OPT_ADAM (utils.py:499-500,
+                            torch.optim.Adam defaults: betas 0.9 / 0.999, eps 1e-8, lr = eta per group)             */
+  float* opt_state;      /* OSM_OPT_ADAM: device [B][19] = {exp_avg[9], exp_avg_sq[9], step}, zero-initialised by the
+                            caller and kept across calls like the reference's optimizer object; NULL for SGD        */
 } osm_guidance_params;
 
 /* replaces Operator.forward (measurements.py:138-151, 251-264, 363-376): out[B,3,HW] = A_phi(x[B,4,HW]).

@@ -395,6 +395,7 @@ class OperatorSpec:
     depth_type: str
     value: tuple
     eta: tuple  # learning rate per phi group, in get_variable_list() order
+    optimizer: str = "sgd"  # 'sgd' / 'GD' (measurements.py:279-303) or 'adam' (utils.py:499-500, torch.optim.Adam defaults)
 
 
 def operator_forward(spec: OperatorSpec, x: torch.Tensor, phis: list) -> torch.Tensor:
@@ -530,8 +531,19 @@ def is_freeze_phi(g: GuidanceSpec, idx: int, T: int) -> bool:
     return idx > g.update_start * T or idx < g.update_end * T
 
 
+def adam_update(p, grad, lr, state):
+    """One torch.optim.Adam step (single-tensor path, defaults betas 0.9 / 0.999, eps 1e-8, no weight decay) on a detached
+    parameter; state = dict(m, v, step) is updated in place.  Bias corrections in Python floats, tensor math in fp32."""
+    state["step"] += 1
+    state["m"] = state["m"] + (grad - state["m"]) * (1 - 0.9)
+    state["v"] = state["v"] * 0.999 + (grad * grad) * (1 - 0.999)
+    bc1, bc2 = 1 - 0.9 ** state["step"], 1 - 0.999 ** state["step"]
+    denom = state["v"].sqrt() / math.sqrt(bc2) + 1e-8
+    return p + (-(lr / bc1)) * (state["m"] / denom)
+
+
 def guided_step(sd, cfg: UNetConfig, tab: Tables, op: OperatorSpec, g: GuidanceSpec, x: torch.Tensor, y: torch.Tensor,
-                phis: list, idx: int, noise: torch.Tensor):
+                phis: list, idx: int, noise: torch.Tensor, opt_state: list | None = None):
     """One iteration of p_sample_loop (gaussian_diffusion.py:213-271) + conditioning (condition_methods.py:146-231).
 
     x [B,4,H,W], y [B,3,H,W], phis list of [B,c,1,1] (updated copies are returned), noise [B,4,H,W].
@@ -555,7 +567,13 @@ def guided_step(sd, cfg: UNetConfig, tab: Tables, op: OperatorSpec, g: GuidanceS
         if last:
             gx = grads[0]
             grads = grads[1:]
-        if not freeze:  # SGD step after every evaluation, incl. the last (measurements.py:266-303)
+        if not freeze and op.optimizer.lower() == "adam":   # optimizer.step() after every evaluation, state kept across calls
+            if opt_state is None:
+                opt_state = []
+            while len(opt_state) < len(ph):
+                opt_state.append(dict(m=torch.zeros_like(ph[len(opt_state)].detach()), v=torch.zeros_like(ph[len(opt_state)].detach()), step=0))
+            phis = [adam_update(p.detach(), gp, eta, stt) for p, eta, gp, stt in zip(ph, op.eta, grads, opt_state)]
+        elif not freeze:  # SGD step after every evaluation, incl. the last (measurements.py:266-303)
             phis = [(p.detach() - eta * gp) for p, eta, gp in zip(ph, op.eta, grads)]
         else:
             phis = [p.detach() for p in ph]
@@ -565,7 +583,7 @@ def guided_step(sd, cfg: UNetConfig, tab: Tables, op: OperatorSpec, g: GuidanceS
     if idx != 0:
         x_next = x_next + torch.exp(0.5 * logvar.detach()) * noise
     return dict(x_next=x_next, pred_xstart=x0.detach(), phis=phis, loss=norm.detach(), grad=gx, mean=mean.detach(),
-                log_variance=logvar.detach(), model_out=out.detach())
+                log_variance=logvar.detach(), model_out=out.detach(), opt_state=opt_state)
 
 
 def guidance_on(g: GuidanceSpec, idx: int, T: int) -> bool:
@@ -778,7 +796,7 @@ def specs_from_config(cfg, B=1):
         names = ["phi_ab", "phi_inf"]
     eta = tuple(float(o.get(n + "_eta", 1e-5)) if o.get(n + "_learn_flag", True) else 0.0 for n in names)
     phis = [torch.tensor(_floats(o[n]), dtype=torch.float32).repeat(B, 1)[..., None, None] for n in names]
-    op = OperatorSpec(kind, o.get("depth_type"), val if len(val) > 1 else val[0], eta)
+    op = OperatorSpec(kind, o.get("depth_type"), val if len(val) > 1 else val[0], eta, str(o.get("optimizer", "sgd")))
     p, sp = cfg["conditioning"]["params"], cfg["sample_pattern"]
     clip = p.get("gradient_clip", "False").split(",")
     g = GuidanceSpec(scale=_floats(p["scale"]), clip=float(clip[1]) if clip[0].strip().lower() == "true" else None,

@@ -420,6 +420,7 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
   __shared__ double red[32 * GUID_NRED + GUID_NRED];
   __shared__ double xslot[2 * GUID_NRED], xtot[GUID_NRED];
   __shared__ float sphi[9];
+  __shared__ float s_m[9], s_v[9], s_step;   // Adam state of this image (every CTA of the cluster keeps an identical copy)
   const int b = blockIdx.x / csize, rank = blockIdx.x % csize;
   int parity = 0;
   const int per = (HW + csize - 1) / csize;
@@ -432,6 +433,11 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
   const bool freeze = freeze_flag[0] != 0;
   const int n_eval = freeze ? 1 : P.n_iter;
   if (threadIdx.x < 9) sphi[threadIdx.x] = phi_io[9 * b + threadIdx.x];
+  const bool adam = P.optimizer == OSM_OPT_ADAM;
+  if (adam) {
+    if (threadIdx.x < 9) { s_m[threadIdx.x] = P.opt_state[19 * b + threadIdx.x]; s_v[threadIdx.x] = P.opt_state[19 * b + 9 + threadIdx.x]; }
+    if (threadIdx.x == 0) s_step = P.opt_state[19 * b + 18];
+  }
 
   // phi-independent reductions: channel means (avrg_loss) and the val_loss sum
   double pre[4] = {0, 0, 0, 0};
@@ -525,23 +531,38 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
     if (!freeze) {
       __syncthreads();
       if (threadIdx.x == 0) {
-        // SGD per group (measurements.py:266-303 / torch.optim.SGD, no momentum)
+        // gradients per phi element in get_variable_list() order (tied operators sum the a and b contributions)
+        float g[9], lr[9];
+        int idx[9], n = 0;
         if (P.op_kind == OSM_OP_UNDERWATER_REVISED) {
-          for (int c = 0; c < 3; ++c) {
-            sphi[c] -= P.eta[0] * (float)(acc[1 + c] * invL);
-            sphi[3 + c] -= P.eta[1] * (float)(acc[4 + c] * invL);
-            sphi[6 + c] -= P.eta[2] * (float)(acc[7 + c] * invL);
-          }
+          for (int c = 0; c < 3; ++c) { g[n] = (float)(acc[1 + c] * invL); lr[n] = P.eta[0]; idx[n++] = c; }
+          for (int c = 0; c < 3; ++c) { g[n] = (float)(acc[4 + c] * invL); lr[n] = P.eta[1]; idx[n++] = 3 + c; }
+          for (int c = 0; c < 3; ++c) { g[n] = (float)(acc[7 + c] * invL); lr[n] = P.eta[2]; idx[n++] = 6 + c; }
         } else if (P.op_kind == OSM_OP_UNDERWATER) {
-          for (int c = 0; c < 3; ++c) {
-            sphi[c] -= P.eta[0] * (float)((acc[1 + c] + acc[4 + c]) * invL);
-            sphi[6 + c] -= P.eta[1] * (float)(acc[7 + c] * invL);
-          }
+          for (int c = 0; c < 3; ++c) { g[n] = (float)((acc[1 + c] + acc[4 + c]) * invL); lr[n] = P.eta[0]; idx[n++] = c; }
+          for (int c = 0; c < 3; ++c) { g[n] = (float)(acc[7 + c] * invL); lr[n] = P.eta[1]; idx[n++] = 6 + c; }
         } else {
-          double s = 0;
-          for (int c = 0; c < 3; ++c) s += acc[1 + c] + acc[4 + c];
-          sphi[0] -= P.eta[0] * (float)(s * invL);
-          for (int c = 0; c < 3; ++c) sphi[6 + c] -= P.eta[1] * (float)(acc[7 + c] * invL);
+          double sab = 0;
+          for (int c = 0; c < 3; ++c) sab += acc[1 + c] + acc[4 + c];
+          g[n] = (float)(sab * invL); lr[n] = P.eta[0]; idx[n++] = 0;
+          for (int c = 0; c < 3; ++c) { g[n] = (float)(acc[7 + c] * invL); lr[n] = P.eta[1]; idx[n++] = 6 + c; }
+        }
+        if (!adam) {
+          // SGD per group (measurements.py:266-303 / torch.optim.SGD, no momentum)
+          for (int k = 0; k < n; ++k) sphi[idx[k]] -= lr[k] * g[k];
+        } else {
+          // torch.optim.Adam (single-tensor path, defaults): step += 1; m = lerp(m, g, 1 - b1); v = b2 v + (1 - b2) g^2;
+          // p -= (lr / (1 - b1^step)) * m / (sqrt(v) / sqrt(1 - b2^step) + eps) - bias corrections in double like the host code
+          s_step += 1.0f;
+          const double bc1 = 1.0 - pow(0.9, (double)s_step), bc2 = 1.0 - pow(0.999, (double)s_step);
+          const float bc2_sqrt = (float)sqrt(bc2);
+          for (int k = 0; k < n; ++k) {
+            const int i = idx[k];
+            s_m[i] = __fadd_rn(s_m[i], __fmul_rn(__fsub_rn(g[k], s_m[i]), (float)(1.0 - 0.9)));
+            s_v[i] = __fadd_rn(__fmul_rn(s_v[i], 0.999f), __fmul_rn(__fmul_rn(g[k], g[k]), (float)(1.0 - 0.999)));
+            const float denom = __fadd_rn(__fdiv_rn(sqrtf(s_v[i]), bc2_sqrt), 1e-8f);
+            sphi[i] = __fadd_rn(sphi[i], __fmul_rn((float)(-(double)lr[k] / bc1), __fdiv_rn(s_m[i], denom)));
+          }
         }
       }
       __syncthreads();
@@ -550,6 +571,10 @@ guidance_phi_loop_kernel(osm_guidance_params P, const float* __restrict__ x0, co
   if (csize > 1) guid_cluster_sync();  // no CTA may exit while a peer can still read its exchange slots
   if (rank != 0) return;
   if (threadIdx.x < 9) phi_io[9 * b + threadIdx.x] = sphi[threadIdx.x];
+  if (adam && !freeze) {
+    if (threadIdx.x < 9) { P.opt_state[19 * b + threadIdx.x] = s_m[threadIdx.x]; P.opt_state[19 * b + 9 + threadIdx.x] = s_v[threadIdx.x]; }
+    if (threadIdx.x == 0) P.opt_state[19 * b + 18] = s_step;
+  }
   if (threadIdx.x == 0) {
     losses[4 * b + 0] = Lnorm;
     losses[4 * b + 1] = avrg_term;
@@ -563,6 +588,8 @@ int guidance_phi_loop_launch(const osm_guidance_params* p, const float* x0, cons
   if (p->op_kind < 0 || p->op_kind > 2) return fail(OSM_ERR_INVALID, "guidance: unknown operator kind");
   if (p->n_iter < 1) return fail(OSM_ERR_INVALID, "guidance: n_iter must be >= 1");
   if (p->loss_kind != OSM_LOSS_NORM && p->loss_kind != OSM_LOSS_MSE) return fail(OSM_ERR_INVALID, "guidance: unknown loss kind");
+  if (p->optimizer != OSM_OPT_SGD && p->optimizer != OSM_OPT_ADAM) return fail(OSM_ERR_INVALID, "guidance: unknown optimizer");
+  if (p->optimizer == OSM_OPT_ADAM && !p->opt_state) return fail(OSM_ERR_INVALID, "guidance: Adam needs its state buffer");
   const int csize = (HW >= GUID_CLUSTER * GUID_THREADS) ? GUID_CLUSTER : 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * csize));

@@ -114,6 +114,8 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
             w = self.aux_loss.kernel_weights() if self.aux_loss is not None else {"gamma_avrg": 0.0, "gamma_val": 0.0}
             p.gamma_avrg, p.gamma_val = w["gamma_avrg"], w["gamma_val"]
             p.loss_kind = 1 if self.loss_function == "mse" else 0
+            p.optimizer = 1 if str(op.optimizer).lower() == "adam" else 0
+            p.opt_state = op.opt_state.data_ptr() if op.opt_state is not None else None
             self._params = p
         return self._params
 

@@ -9,8 +9,8 @@ Mirrors the registries and classes of the reference `guided_diffusion/measuremen
 Difference in mechanics, not in results: the water parameters of all images live in ONE device tensor
 `phi[B, 9] = {a | b | inf}` that the fused guidance kernel (osm_guidance_phi_loop) reads and updates in place;
 `phi_a`, `phi_b`, `phi_inf`, `phi_ab` are views of it with the reference's [B, c, 1, 1] shapes.  The SGD step
-(`optimizer: sgd` / `GD`, lr = phi_*_eta, 0 when the learn flag is off; :240-249, :266-303) is part of that
-kernel, so `optimize()` only reports the current values.
+(`optimizer: sgd` / `GD` / `adam`, lr = phi_*_eta, 0 when the learn flag is off; :240-249, :266-303, utils.py:494-500) is part
+of that kernel, so `optimize()` only reports the current values.
 """
 from __future__ import annotations
 
@@ -126,9 +126,12 @@ class LearnableOperator:
         optimizer = kwargs.get("optimizer", None)
         if optimizer is None:
             raise AttributeError("'NoneType' object has no attribute 'lower'")  # utils.py:495 behaviour: key must exist
-        if optimizer.lower() not in ("", "gd", "sgd"):
-            raise ValueError(f"Optimizer '{optimizer}' is not supported by the fused phi update (sgd / GD only).")
+        if optimizer.lower() not in ("", "gd", "sgd", "adam"):
+            raise ValueError(f"Optimizer '{optimizer}' is not supported by the fused phi update (sgd / GD / adam).")
         self.optimizer = optimizer
+        # torch.optim.Adam's per-parameter state (exp_avg[9], exp_avg_sq[9], step), kept across conditioning calls like the
+        # reference's optimizer object (measurements.py:240-249)
+        self.opt_state = torch.zeros(batch_size, 19, dtype=torch.float32, device=self.device) if optimizer.lower() == "adam" else None
         row = torch.zeros(9, dtype=torch.float32)
         for off, vals in init:
             row[off:off + len(vals)] = torch.tensor(vals, dtype=torch.float32)

@@ -96,6 +96,25 @@ def main():
         for k, v in vd.items():
             out[f"mse/step{idx}/{k}"] = v.detach().numpy()
         print("mse", idx, "freeze", freeze, loss)
+    # ---------------------------------------------------------------- Adam for phi (utils.py:499-500): two consecutive
+    # optimised steps with ONE operator, so the optimizer state carries over as in a sampling run
+    cfg = yaml.load(open(os.path.join(ROOT, "configs", MSE_CASE["yaml"])), Loader=yaml.FullLoader)
+    cfg["diffusion"]["timestep_respacing"] = MSE_CASE["respacing"]
+    sampler = create_sampler(**cfg["diffusion"])
+    opcfg = dict(cfg["measurement"]["operator"]); opcfg["batch_size"] = 1; opcfg["optimizer"] = "adam"
+    op = get_operator(device="cpu", **opcfg)
+    cond = get_conditioning_method(cfg["conditioning"]["method"], op, get_noise(**cfg["measurement"]["noise"]),
+                                   **cfg["conditioning"]["params"], **cfg["sample_pattern"], **cfg["aux_loss"])
+    for idx in (2, 1):
+        img = case_inputs(f"x:osmosis:{idx}").clone().requires_grad_(True)
+        o = sampler.p_mean_variance(model, img, torch.tensor([idx]))
+        x_t, loss, vd, grads, aux = cond.conditioning(x_t=o["mean"], measurement=y_meas, noisy_measurement=None, x_prev=img,
+                                                      x_0_hat=o["pred_xstart"], freeze_phi=False, time_index=float(idx) / T)
+        out[f"adam/step{idx}/x_t"] = x_t.detach().numpy()
+        out[f"adam/step{idx}/loss"] = np.asarray(loss, dtype=np.float32)
+        for k, v in vd.items():
+            out[f"adam/step{idx}/{k}"] = v.detach().numpy().copy()
+        print("adam", idx, loss, {k: v.flatten().tolist() for k, v in vd.items()})
     # ---------------------------------------------------------------- every mean / variance processor of the registries
     from guided_diffusion.posterior_mean_variance import get_mean_processor, get_var_processor
     from tests.golden.cases import PROC_CASES, proc_inputs

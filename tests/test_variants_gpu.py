@@ -217,3 +217,32 @@ def test_registries_expose_the_variants():
     assert type(s).__name__ == "DDIM" and s.num_timesteps == 8 and s.mean_processor.clip_denoised
     with pytest.raises(NotImplementedError):
         get_conditioning_method("osmosis", None, None, gradient_x_prev=False)
+
+
+def test_adam_phi_optimizer_vs_reference_golden():
+    """`optimizer: adam` in the fused guidance kernel: two consecutive optimised steps (2 x 20 Adam updates, state carried in
+    the operator) against the reference's torch.optim.Adam run; and the batch semantics (per-image state)."""
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import is_freeze_phi
+    cfg = load_yaml_cfg(MSE_CASE["yaml"], MSE_CASE["respacing"])
+    m = model("fp32")
+    y, _ = case_inputs("meas:osmosis")
+    for B in (1, 2):
+        opcfg = dict(cfg["measurement"]["operator"]); opcfg["batch_size"] = B; opcfg["optimizer"] = "adam"
+        op = get_operator(device=DEV, **opcfg)
+        cond = get_conditioning_method(cfg["conditioning"]["method"], op, get_noise(**cfg["measurement"]["noise"]),
+                                       **cfg["conditioning"]["params"], **cfg["sample_pattern"], **cfg["aux_loss"])
+        sampler = create_sampler(**cfg["diffusion"])
+        for idx in (2, 1):
+            x = case_inputs(f"x:osmosis:{idx}").to(DEV).repeat(B, 1, 1, 1)
+            st = sampler.fused_state(m, cond, x, y.to(DEV).repeat(B, 1, 1, 1))
+            assert not is_freeze_phi(cfg["sample_pattern"], idx, sampler.num_timesteps)
+            st["t_idx"].fill_(idx); st["t_model"].fill_(sampler._model_timestep(idx)); st["freeze"].fill_(0)
+            img = x.clone()
+            sampler.fused_step(m, cond, st, img, torch.zeros_like(img))
+            torch.cuda.synchronize()
+            pre = f"adam/step{idx}/"
+            for b in range(B):
+                assert rel_err(st["losses"][b:b + 1, 0].cpu(), GOLD[pre + "loss"]) < 1e-4
+                for n in op.groups:
+                    assert maxdiff(getattr(op, n)[b:b + 1].cpu(), GOLD[pre + n]) < 3e-6, (B, idx, n)
+        assert float(op.opt_state[:, 18].min()) == 40.0 and float(op.opt_state[:, 18].max()) == 40.0

@@ -93,3 +93,25 @@ def test_every_mean_and_variance_processor_matches_the_reference_registries():
             assert np.array_equal(np.isinf(lv), np.isinf(want)), key
             fin = np.isfinite(want)
             assert float(np.abs(lv[fin] - want[fin]).max(initial=0.0)) <= 1e-6 * max(1.0, float(np.abs(want[fin]).max(initial=0.0))), key
+
+
+def test_adam_phi_optimizer_two_consecutive_steps():
+    """`optimizer: adam` for phi (utils.py:499-500): 2 x 20 Adam steps with the state carried from one sampling step to the
+    next, against the reference's torch.optim.Adam run."""
+    cfg = load_yaml_cfg(MSE_CASE["yaml"], MSE_CASE["respacing"])
+    cfg["measurement"]["operator"]["optimizer"] = "adam"
+    tab, op, gs, phis, names = oracle_specs_from_cfg(cfg)
+    assert op.optimizer == "adam"
+    y, _ = case_inputs("meas:osmosis")
+    state = None
+    for idx in (2, 1):
+        x = case_inputs(f"x:osmosis:{idx}")
+        r = orc.guided_step(small_state_dict(), small_cfg(), tab, op, gs, x, y, phis, idx, torch.zeros_like(x), opt_state=state)
+        phis, state = r["phis"], r["opt_state"]
+        pre = f"adam/step{idx}/"
+        assert rel_err(r["loss"], GOLD[pre + "loss"]) < 1e-4
+        for n, p in zip(names, phis):
+            assert maxdiff(p, GOLD[pre + n]) < 2e-6, (idx, n)
+        x_t = r["mean"] - torch.tensor(gs.scale)[None, :, None, None] * torch.clamp(r["grad"], -gs.clip, gs.clip)
+        assert maxdiff(x_t, GOLD[pre + "x_t"]) < 2e-5 * max(1.0, float(np.abs(GOLD[pre + "x_t"]).max()))
+    assert state[0]["step"] == 40
