@@ -248,7 +248,7 @@ def run_native(args):
     roofline["other_kernels"] = extra
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True,
                scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
-               config=dict(workload=f"osmosis_sample_config.yaml, batch {B} per GPU, {args.size}x{args.size} RGBD, 1000-step guided "
+               config=dict(workload=f"{os.path.basename(args.config)}, batch {B} per GPU, {args.size}x{args.size} RGBD, 1000-step guided "
                                     f"chain timed on {K} consecutive steps of a {K + W}-step respacing", batch_per_gpu=B,
                            global_batch=B * world, image=args.size, unet_params=model.num_params(), parallelism=f"dp{world} (batch-sharded, no collective)",
                            l2="per-step working set (2.2 GB weights + 1.6 GB activations per image) exceeds the 126 MB L2"),
@@ -332,7 +332,7 @@ def run_reference(args):
               f"threads, oracle port of the reference (its Python cannot travel to the GPU box)")
     out = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=len(ts), warmup=min(args.warmup, 1),
                ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-               config=dict(workload=f"osmosis_sample_config.yaml, batch 1, {args.size}x{args.size} RGBD, 1000-step guided chain "
+               config=dict(workload=f"{os.path.basename(args.config)}, batch 1, {args.size}x{args.size} RGBD, 1000-step guided chain "
                                     f"(extrapolated from {len(ts)} timed steps)", image=args.size),
                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
