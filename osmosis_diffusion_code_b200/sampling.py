@@ -93,8 +93,14 @@ def run_sampling(args, device=None, batch_per_rank: int = 1, rank: int = 0, worl
         sample, variable_dict, loss, out_xstart = out
         post = utilso.postprocess_samples(operator, out_xstart, ref_img)
         norm_loss = post["norm_loss"].cpu().numpy()
+        psnr = None
+        if "gt_rgb" in extras:    # simulation sets (ImagesFolder_GT): PSNR of the restored RGB against the ground truth, in [0, 1]
+            mse = ((post["sample_rgb_01_clip"] - 0.5 * (extras["gt_rgb"] + 1)) ** 2).mean(dim=(1, 2, 3))
+            psnr = (10 * torch.log10(1.0 / mse.clamp_min(1e-12))).cpu().numpy()
         for k, n in enumerate(names):
             r = dict(name=n, loss=float(loss[k]), norm_loss=float(np.round(norm_loss[k], 3)))
+            if psnr is not None:
+                r["psnr_rgb"] = float(psnr[k])
             for key, v in variable_dict.items():
                 r[key] = [round(float(t), 3) for t in v[k].flatten().cpu()]
             results.append(r)
