@@ -137,3 +137,44 @@ def test_full_guided_step_of_each_config(cfg_name):
         moved = float((op.phi - phi_before).abs().max())
         assert (moved == 0.0) if freeze else (moved > 0.0)
         assert float((st["losses"][0] - st["losses"][1]).abs().max()) > 0    # distinct images -> distinct per-image losses
+
+
+def test_full_size_chain_psnr_product_vs_exact_mode():
+    """BASELINE config 4's check at full size (osmosis_simulation_sample_config, 256x256, 553 M parameters, a batch of two
+    synthetic scenes): a 12-step respaced guided chain in product mode (tcgen05 TF32 convs / fused attention / fused GroupNorm
+    statistics) against the same chain in exact mode (fp32 CUDA-core convs, fp32-accurate attention) with identical injected
+    noise - PSNR of the restored RGB (pred_xstart[:, :3], data range 2.0) per image, and phi.  Free-running chains separate
+    through clamp sign flips (the reference against its own fp64 twin reaches 55 dB after 250 steps)."""
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    a = arguments_from_file(os.path.join(ROOT, "configs", "osmosis_simulation_sample_config.yaml"))
+    B, T = 2, 12
+    opc0 = dict(a.measurement["operator"])
+    ph = lambda k: [float(v) for v in str(opc0[k]).split(",")]
+    y = torch.cat([synth_measurement(20 + i, S, ph("phi_ab"), ph("phi_ab"), ph("phi_inf"), depth_type=opc0.get("depth_type"))[0]
+                   for i in range(B)]).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    x_T = torch.randn(1, 4, S, S, generator=g).repeat(B, 1, 1, 1).to(DEV)
+    noises = [torch.randn(1, 4, S, S, generator=g).repeat(B, 1, 1, 1).to(DEV) for _ in range(T)]
+    res = {}
+    for mode in ("fp32", "tc"):
+        m = full_model(mode)
+        opc = dict(opc0); opc["batch_size"] = B
+        op = get_operator(device=DEV, **opc)
+        cond = get_conditioning_method(a.conditioning["method"], op, get_noise(**a.measurement["noise"]), **a.conditioning["params"],
+                                       **a.sample_pattern, **a.aux_loss)
+        d = dict(a.diffusion); d["timestep_respacing"] = T
+        sampler = create_sampler(**d)
+        img = x_T.clone()
+        stepper = FusedStepper(sampler, m, cond, img, y, a.sample_pattern, cuda_graph=(mode == "tc"))
+        for k, idx in enumerate(range(T)[::-1]):
+            stepper._draw_into = lambda buf, _k=k: buf.copy_(noises[_k]) if buf.shape[1] == 4 else buf.zero_()
+            stepper.step(idx)
+        torch.cuda.synchronize()
+        res[mode] = (stepper.st["x0"].clone(), op.phi.clone(), stepper.st["losses"].clone())
+        assert torch.isfinite(res[mode][0]).all()
+    mse = ((res["tc"][0][:, :3] - res["fp32"][0][:, :3]) ** 2).mean(dim=(1, 2, 3))
+    psnr = 10 * torch.log10(4.0 / mse)
+    print("full-size 12-step chain PSNR (dB) product vs exact mode:", [round(float(v), 1) for v in psnr])
+    assert float(psnr.min()) > 50.0, psnr        # measured 86 dB on B200
+    assert float((res["tc"][1] - res["fp32"][1]).abs().max()) < 1e-3
+    assert rel_err(res["tc"][2][:, 0].cpu(), res["fp32"][2][:, 0].cpu()) < 5e-2
