@@ -113,14 +113,57 @@ def run_sampling(args, device=None, batch_per_rank: int = 1, rank: int = 0, worl
     return results
 
 
+def run_prior_sampling(args, device=None, out_dir: str | None = None, model=None, image_size: int | None = None):
+    """The body of the reference's `RGBD_prior_sampling.py:main` (:56-122, BASELINE config 1): `number_of_images` unguided RGBD
+    samples through `osmosis_utils.diffusion.GaussianDiffusion.inverse`.  Returns a list of dicts {x [1,4,S,S] on the device,
+    x_start_rgb, x_start_depth} and writes <out_dir>/{single_images/rgb, single_images/depth, grid_results}/image_<i>.png
+    like the reference when `args.save_singles` / `args.save_grids` are set."""
+    from .osmosis_utils.diffusion import GaussianDiffusion
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if model is None:
+        model = create_model(**args.unet_model).to(dev).eval()
+    S = int(image_size if image_size is not None else getattr(args, "image_size", args.unet_model["image_size"]))
+    x_start_dim = 4 if args.unet_model["pretrain_model"] == "osmosis" else 3
+    rgb_dir = depth_dir = grid_dir = None
+    if out_dir is not None:
+        rgb_dir, depth_dir, grid_dir = pjoin(out_dir, "single_images", "rgb"), pjoin(out_dir, "single_images", "depth"), pjoin(out_dir, "grid_results")
+        for d in (rgb_dir, depth_dir, grid_dir):
+            os.makedirs(d, exist_ok=True)
+    torch.manual_seed(args.manual_seed)                                   # once, before the loop (:83)
+    results = []
+    for im_idx in range(args.number_of_images):
+        diffusion = GaussianDiffusion(T=args.diffusion["steps"], schedule=args.diffusion["noise_schedule"])
+        x, (x_start_rgb, x_start_depth) = diffusion.inverse(
+            net=model, shape=(x_start_dim, S, S), image_channels=x_start_dim, steps=args.diffusion["timestep_respacing"], device=dev,
+            record_process=getattr(args, "record_process", False), record_every=getattr(args, "record_every", 200),
+            save_path=grid_dir, image_idx=im_idx)
+        results.append(dict(x=x, x_start_rgb=x_start_rgb, x_start_depth=x_start_depth))
+        if out_dir is None:
+            continue
+        if getattr(args, "save_singles", False) and x_start_rgb is not None:
+            _save_png(x_start_rgb, pjoin(rgb_dir, f"image_{im_idx}.png"))
+            if x_start_depth is not None:
+                _save_png(x_start_depth, pjoin(depth_dir, f"image_{im_idx}.png"))
+        if getattr(args, "save_grids", False) and x_start_dim == 4:
+            x_rgb = 0.5 * (1 + x[0, 0:3])
+            x_d_pmm = utilso.min_max_norm_range_percentile(x[:, 3].contiguous(), percent_low=0.05, percent_high=0.99)
+            _save_png(torch.cat([x_rgb, utilso.depth_tensor_to_color_image(x_d_pmm)], dim=2), pjoin(grid_dir, f"image_{im_idx}.png"))
+    return results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("-c", "--config_file", default="./configs/osmosis_sample_config.yaml")
     ap.add_argument("-d", "--device", default=0, type=int)
     ap.add_argument("--batch", default=1, type=int, help="images per GPU per sampling run")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--prior", action="store_true", help="unguided RGBD prior sampling (RGBD_prior_sampling.py, RGBD_sample_config.yaml)")
     a = ap.parse_args()
     args = utilso.arguments_from_file(os.path.abspath(a.config_file))
+    if a.prior:
+        torch.cuda.set_device(a.device)
+        run_prior_sampling(args, device=f"cuda:{a.device}", out_dir=a.out or pjoin(os.path.abspath(args.save_dir), "rgbd_prior"))
+        return
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(a.device)))
     torch.cuda.set_device(local)

@@ -52,3 +52,22 @@ def test_end_to_end_run_is_batch_and_shard_invariant(cfg_name, tmp_path):
             if k.startswith("phi"):
                 assert np.allclose(r[k], s[k], atol=2e-3), (k, r[k], s[k])
     assert len({round(r["loss"], 4) for r in one}) == 3               # distinct images -> distinct losses
+
+
+def test_prior_sampling_run(tmp_path):
+    """BASELINE config 1 end to end (`run_prior_sampling`, the body of RGBD_prior_sampling.py:main): RGBD_sample_config.yaml
+    with the small UNet and a 6-step chain; seeded once, so two images differ and a re-run reproduces them."""
+    from osmosis_diffusion_code_b200.sampling import run_prior_sampling
+    a = arguments_from_file(os.path.join(ROOT, "configs", "RGBD_sample_config.yaml"))
+    a.diffusion = dict(a.diffusion); a.diffusion.update(steps=6, timestep_respacing=6)
+    a.number_of_images = 2
+    m = model("fp32")
+    r1 = run_prior_sampling(a, device=DEV, model=m, image_size=32, out_dir=str(tmp_path / "p"))
+    r2 = run_prior_sampling(a, device=DEV, model=m, image_size=32)
+    assert len(r1) == 2 and r1[0]["x"].shape == (1, 4, 32, 32) and torch.isfinite(r1[0]["x"]).all()
+    assert not torch.equal(r1[0]["x"], r1[1]["x"])
+    assert torch.equal(r1[0]["x"], r2[0]["x"]) and torch.equal(r1[1]["x"], r2[1]["x"])
+    assert r1[0]["x_start_rgb"].shape == (3, 32, 32) and float(r1[0]["x_start_rgb"].min()) >= 0
+    for sub in ("single_images/rgb", "single_images/depth", "grid_results"):
+        names = sorted(os.listdir(tmp_path / "p" / sub))
+        assert "image_0.png" in names and "image_1.png" in names
