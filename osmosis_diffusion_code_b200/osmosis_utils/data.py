@@ -100,6 +100,8 @@ def preprocess_batch(images, device=None, size: int = IMAGE_SIZE, degamma: bool 
             raise ValueError(f"expected uint8 [H,W,3] or [H,W] images, got {a.dtype} {a.shape}")
         arrs.append(np.ascontiguousarray(a))
     B = len(arrs)
+    if B == 0:   # a rank whose shard of the last global batch is empty
+        return out if out is not None else torch.empty(0, 3, size, size, dtype=torch.float32, device=dev)
     offs = np.cumsum([0] + [(a.size + 255) // 256 * 256 for a in arrs])
     stage = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
     sv = stage.numpy()

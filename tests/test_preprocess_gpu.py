@@ -25,6 +25,22 @@ def test_batch_of_mixed_sizes_matches_oracle_bit_exactly_and_reference_golden():
         assert pre_check(GOLD, n, out[k], 0.0 if n != "big720x1280" else 5e-7), n
 
 
+def test_empty_and_extreme_inputs():
+    """An empty batch (a rank with no images left), a 1-pixel-high strip, a constant image and the saturated values."""
+    from osmosis_diffusion_code_b200.osmosis_utils.data import preprocess_batch
+    assert tuple(preprocess_batch([]).shape) == (0, 3, 256, 256)
+    strip = np.full((1, 700, 3), 200, np.uint8)                     # up-scaled 256x vertically, cropped horizontally
+    const = np.full((300, 300), 0, np.uint8)                        # grey, all black -> -1
+    white = np.full((256, 256, 3), 255, np.uint8)                   # identity size, all white -> +1
+    out = preprocess_batch([strip, const, white]).cpu().numpy()
+    for k, img in enumerate((strip, const, white)):
+        assert np.array_equal(out[k], orc.preprocess_image(img)), k
+    assert np.all(out[1] == -1.0) and np.all(out[2] == 1.0)
+    assert np.allclose(out[0], 2 * np.float32(200) / 255 - 1, atol=3e-7)
+    big = np.random.RandomState(1).randint(0, 256, (1500, 2100, 3)).astype(np.uint8)     # 5.9x down-scale: 13-tap filters
+    assert np.array_equal(preprocess_batch([big]).cpu().numpy()[0], orc.preprocess_image(big))
+
+
 def test_degamma_fused_and_standalone():
     from osmosis_diffusion_code_b200.osmosis_utils.data import preprocess_batch, degamma_input
     imgs = [pre_inputs("land300x400"), pre_inputs("up200x320")]
