@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Headline benchmark: 256x256 RGBD images/sec for a 1000-step guided sampling run (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # native sm_100a path (one process per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    python bench.py --gpus N --steps K --warmup W               # native sm_100a path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W       # the UNMODIFIED reference (baseline/_ref) on the host CPU
+    python bench.py --impl reference-gpu --steps K --warmup W   # the same unmodified reference in eager CUDA on cuda:0
 
 A "step" is ONE guided reverse step of the osmosis_sample_config chain over the whole batch: UNet forward, posterior,
 the phi-optimisation / guidance kernel, UNet input-VJP, clamped update + noise.  The chain is the config's sampler
@@ -16,10 +17,17 @@ architecture and a physically consistent measurement (osmosis_diffusion_code_b20
           re-uploaded every step, and the step's loss read back to the host every step (as the reference's progress bar
           does; the read of step k completes while step k+1 runs), plus the final pred_xstart device->host copy.  W untimed
           warm-up steps go through the same API first (graph capture happens there, once per sampler).
-Both arms print ONE JSON line on rank 0.
+  configs : the other BASELINE.json configurations, device-resident, in the same line: config 3 (batch 32 on one GPU),
+          config 4 (simulation config, 32 images per GPU = batch 256 on 8 GPUs, finished by an NCCL all-gather of the samples
+          and a PSNR of two restored images against the unmodified reference run in eager CUDA on the same GPU) and config 5
+          (haze config, 32 images per GPU = batch 128 on 4 GPUs, 250-step respacing, de-gamma'd input).
+  gpu_eager_reference : the unmodified reference timed in eager CUDA (cuDNN TF32) on the same GPU, batch 1 - the
+          "same algorithm, stock kernels" bar.
+All arms print ONE JSON line on rank 0.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -118,9 +126,146 @@ def respaced(a, n_steps):
     return create_sampler(**d)
 
 
+def workload_name(config, B, size, chain_steps, K, T):
+    """The same wording in every arm, so that the driver can see that the arms ran the same workload."""
+    return (f"{os.path.basename(config)}, batch {B} per GPU, {size}x{size} RGBD, {chain_steps}-step guided chain timed on {K} "
+            f"consecutive steps of a {T}-step respacing")
+
+
+def _phis(opc, k, dflt):
+    return [float(v) for v in str(opc.get(k, dflt)).split(",")]
+
+
+def case_objects(a, dev, B, size, first_image=0, stride=1):
+    """operator / conditioning / measurement of `B` synthetic scenes (first_image, first_image + stride, ...) for config `a`."""
+    from osmosis_diffusion_code_b200.guided_diffusion.measurements import get_operator, get_noise
+    from osmosis_diffusion_code_b200.guided_diffusion.condition_methods import get_conditioning_method
+    from osmosis_diffusion_code_b200.osmosis_utils import data as datao
+    from osmosis_diffusion_code_b200.synthetic import synth_measurement
+    opc = dict(a.measurement["operator"]); opc["batch_size"] = B
+    op = get_operator(device=dev, **opc)
+    cond = get_conditioning_method(a.conditioning["method"], op, get_noise(**a.measurement["noise"]), **a.conditioning["params"],
+                                   **a.sample_pattern, **a.aux_loss)
+    pa, pb = (_phis(opc, "phi_a", "1"), _phis(opc, "phi_b", "1")) if "phi_a" in opc else (_phis(opc, "phi_ab", "1"),) * 2
+    y = torch.cat([synth_measurement(first_image + i * stride, size, pa, pb, _phis(opc, "phi_inf", "0.2,0.4,0.7"),
+                                     depth_type=opc.get("depth_type"))[0] for i in range(B)], 0).to(dev)
+    if getattr(a, "degamma_input", False):
+        y = datao.degamma_input(y)                  # osmosis_sampling.py:173-175
+    return op, cond, y
+
+
+def time_case(model, cfg_path, dev, B, K, W, size, rank, world, local, chain_steps=None, cuda_graph=True, keep=False):
+    """Device-resident timing of one BASELINE configuration: W warm-up + K timed guided steps of the config's chain respaced
+    to W + K steps, B images per GPU; max over ranks.  Returns (row dict, objects kept for the caller when keep)."""
+    import torch.distributed as dist
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import arguments_from_file
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    a = arguments_from_file(cfg_path)
+    base_T = int(a.diffusion["steps"])
+    chain = int(chain_steps or a.diffusion.get("timestep_respacing") or base_T)
+    # images of rank r: r, r + world, ... (sharding.shard_indices)
+    op, cond, y = case_objects(a, dev, B, size, first_image=rank, stride=world)
+    sampler = respaced(a, min(K + W, base_T))
+    T = sampler.num_timesteps
+    torch.manual_seed(a.manual_seed)
+    img = torch.randn(B, 4, size, size, device=dev)
+    stepper = FusedStepper(sampler, model, cond, img, y, a.sample_pattern, cuda_graph=cuda_graph)
+    idxs = [T - 1 - (i % T) for i in range(W + K)]
+    for idx in idxs[:W]:
+        stepper.step(idx)
+    clocks = ClockSampler(local) if rank == 0 else None
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    if clocks: clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for idx in idxs[W:]:
+        stepper.step(idx)
+    e1.record()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms[0]) / K
+    clk = clocks.stop() if clocks else None
+    row = dict(config=os.path.basename(cfg_path), batch_per_gpu=B, global_batch=B * world, chain_steps=chain,
+               workload=workload_name(cfg_path, B, size, chain, K, T), ms_per_step=ms_step,
+               ms_per_image_step=ms_step / B, images_per_s=world * B / (chain * ms_step / 1e3), clocks=clk,
+               finite=bool(torch.isfinite(img).all()), workspace_gb=round(model.workspace_bytes(B, size, size) / 1e9, 2))
+    return row, (dict(a=a, op=op, cond=cond, y=y, stepper=stepper, img=img) if keep else None)
+
+
+def gather_finished(kept, B, world, dev):
+    """The one optional collective of the path: all-gather of the finished samples, phi and losses over NCCL.
+    Returns its device time in ms (max over ranks) and the gathered shape."""
+    import torch.distributed as dist
+    from osmosis_diffusion_code_b200 import sharding
+    st = kept["stepper"].st
+    x0, phi, loss = st["x0"].contiguous(), kept["op"].phi.detach().contiguous(), st["losses"][:, 0].contiguous()
+    n = B * world
+    sharding.gather_images(loss, n)        # warm the communicator
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gx0 = sharding.gather_images(x0, n); gphi = sharding.gather_images(phi, n); gl = sharding.gather_images(loss, n)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = bool(torch.equal(gx0[dist.get_rank()::world], x0)) and tuple(gphi.shape) == (n, 9) and gl.numel() == n
+    return dict(ms=float(t[0]), bytes_per_rank=int(x0.numel() * 4 + phi.numel() * 4 + loss.numel() * 4),
+                gathered=list(gx0.shape), own_rows_intact=ok, backend="nccl")
+
+
+def psnr_vs_reference_gpu(model, cfg_path, dev, size, n_images, T, cuda_graph=True):
+    """BASELINE config 4's check: final pred_xstart[:, :3] of `n_images` scenes sampled here as ONE batch (shared x_T and
+    step noise, i.e. what the reference's per-image reseed gives) against the unmodified reference run per image in eager
+    CUDA on this GPU (cuDNN TF32), both free-running from `manual_seed` over the same T-step respaced chain.  Data range 2."""
+    from baseline import ref_driver as rd
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import arguments_from_file
+    a = arguments_from_file(cfg_path)
+    op, cond, y = case_objects(a, dev, n_images, size)
+    sampler = respaced(a, T)
+    torch.manual_seed(a.manual_seed)
+    x_start = torch.randn(1, 4, size, size, device=dev).expand(n_images, -1, -1, -1).contiguous()
+    _img, _vd, _loss, x0 = sampler.p_sample_loop(model=model, x_start=x_start, measurement=y, measurement_cond_fn=cond.conditioning,
+                                                 record=False, save_root=None, pretrain_model="osmosis", rgb_guidance=False,
+                                                 sample_pattern=a.sample_pattern, noise_mode="shared", cuda_graph=cuda_graph)
+    R = rd.import_reference()
+    rargs = R.utils.arguments_from_file(cfg_path)
+    rargs.diffusion = dict(rargs.diffusion); rargs.diffusion["timestep_respacing"] = T
+    rmodel = rd.reference_model(rargs, dev)
+    out = []
+    import contextlib
+    for i in range(n_images):
+        roperator, rcond, rsampler = rd.reference_pieces(rargs, dev, batch=1)
+        torch.manual_seed(rargs.manual_seed)
+        xs = torch.randn([1, 4, size, size], device=dev).requires_grad_()
+        with contextlib.redirect_stderr(open(os.devnull, "w")):
+            _i, _v, _l, rx0 = rsampler.p_sample_loop(model=rmodel, x_start=xs, measurement=y[i:i + 1], measurement_cond_fn=rcond.conditioning,
+                                                     pretrain_model="osmosis", rgb_guidance=False, sample_pattern=rargs.sample_pattern,
+                                                     record=False, save_root=None, image_idx=i, record_every=200,
+                                                     original_file_name="bench", save_grids_path=None, global_iteration=0)
+        mse = float(((x0[i, :3].double() - rx0[0, :3].double()) ** 2).mean())
+        out.append(round(10 * math.log10(4.0 / max(mse, 1e-30)), 2))
+    del rmodel
+    torch.cuda.empty_cache()
+    return dict(psnr_db=out, images=n_images, chain=f"{T}-step respacing of {os.path.basename(cfg_path)}, free-running from manual_seed",
+                against="unmodified reference (baseline/_ref) in eager CUDA on the same GPU, cuDNN TF32 convolutions", data_range=2.0)
+
+
+def gpu_eager_reference(args, K, W):
+    from baseline import ref_driver as rd
+    r = rd.time_reference_chain(args.config, "cuda", steps=K, warmup=W, size=args.size)
+    t = sum(r["step_s"]) / len(r["step_s"])
+    torch.cuda.empty_cache()
+    return dict(ms_per_step=t * 1e3, images_per_s=1.0 / (1000.0 * t), steps=len(r["step_s"]), warmup=W, batch=1,
+                how="unmodified reference (baseline/_ref) p_sample_loop in eager CUDA on the same GPU, cuDNN default (TF32 convs), "
+                    "host clock between UNet calls after a device sync", finite=r["finite"])
+
+
 def run_native(args):
     import torch.distributed as dist
-    from osmosis_diffusion_code_b200.osmosis_utils.utils import is_freeze_phi
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -131,6 +276,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, K, W = args.batch, args.steps, args.warmup
+    graph = not args.no_cuda_graph
     a, model, op, cond, _, y = build_native(args, dev, B)
     base_T = int(a.diffusion["steps"])
     sampler = respaced(a, min(K + W, base_T))    # K + W > 1000: the full chain, indices wrap around
@@ -138,7 +284,7 @@ def run_native(args):
     torch.manual_seed(a.manual_seed)
     img = torch.randn(B, 4, args.size, args.size, device=dev)
     from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
-    stepper = FusedStepper(sampler, model, cond, img, y, a.sample_pattern, cuda_graph=not args.no_cuda_graph)
+    stepper = FusedStepper(sampler, model, cond, img, y, a.sample_pattern, cuda_graph=graph)
     step = stepper.step
 
     def barrier():
@@ -167,7 +313,6 @@ def run_native(args):
     clk = clocks.stop() if clocks else None
     finite = bool(torch.isfinite(img).all())
     # ---- e2e through the public API, host buffers ----
-    from tools.profile_step import build as _b  # noqa: F401
     from osmosis_diffusion_code_b200.guided_diffusion.measurements import get_operator, get_noise
     from osmosis_diffusion_code_b200.guided_diffusion.condition_methods import get_conditioning_method
     opc = dict(a.measurement["operator"]); opc["batch_size"] = B
@@ -181,7 +326,7 @@ def run_native(args):
     x_start = torch.randn(B, 4, args.size, args.size, device=dev)
     host_loss = []
     loop_kw = dict(model=model, measurement=y_host, measurement_cond_fn=cond2.conditioning, record=False, save_root=None,
-                   pretrain_model="osmosis", rgb_guidance=False, sample_pattern=a.sample_pattern, cuda_graph=not args.no_cuda_graph)
+                   pretrain_model="osmosis", rgb_guidance=False, sample_pattern=a.sample_pattern, cuda_graph=graph)
     # untimed warm-up through the same API (W steps): the sampler keeps its device state and the captured step graph
     # between p_sample_loop calls, as it does between the images of a sampling run
     samp2.p_sample_loop(x_start=x_start, max_steps=min(W, Te), progress=lambda idx, loss: None, **loop_kw)
@@ -205,13 +350,78 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(times[0]), float(times[1])
-    if rank != 0:
-        if world > 1: dist.destroy_process_group()
-        return
     ms_step = ms / K
     value = world * B / (1000.0 * ms_step / 1e3)
     e2e_value = world * B / (1000.0 * (e2e_ms / K) / 1e3)
-    # ---- roofline of the dominant kernel: the 3x3 conv 256->256 @ 256x256 (tcgen05 implicit GEMM) ----
+    roofline, fl, bl = None, 0, 0
+    if rank == 0:
+        roofline, fl, bl = dominant_roofline(args, model, dev)
+    # ---- the other BASELINE configurations (device-resident, same K / W), every rank takes part ----
+    table, gather, psnr, eager, errors = [], None, None, None, {}
+    del stepper, samp2, cond2, op2
+    if not args.no_table:
+        TB = args.table_batch
+        cfgd = os.path.join(ROOT, "configs")
+        cases = [("config 3: batch 32 on one GPU", args.config, None), ("config 4: simulation, 32 images / GPU (batch 256 on 8 GPUs)",
+                 os.path.join(cfgd, "osmosis_simulation_sample_config.yaml"), None),
+                 ("config 5: haze, 32 images / GPU (batch 128 on 4 GPUs), 250-step respacing, de-gamma'd input",
+                  os.path.join(cfgd, "osmosis_haze_sample_config.yaml"), 250)]
+        for name, cpath, chain in cases:
+            try:
+                is_sim = "simulation" in cpath
+                row, kept = time_case(model, cpath, dev, TB, K, W, args.size, rank, world, local, chain_steps=chain, cuda_graph=graph,
+                                      keep=is_sim and world > 1)
+                row["baseline_config"] = name
+                if kept is not None:
+                    gather = gather_finished(kept, TB, world, dev)
+                    del kept
+                table.append(row)
+            except Exception as e:   # a table row must not cost the headline number
+                errors[name] = f"{type(e).__name__}: {e}"
+                barrier()
+    if rank == 0:
+        from baseline import ref_driver as rd
+        if rd.available() and not args.no_eager_reference:
+            try:
+                psnr = psnr_vs_reference_gpu(model, os.path.join(ROOT, "configs", "osmosis_simulation_sample_config.yaml"), dev, args.size,
+                                             2, min(K + W, base_T), cuda_graph=graph)
+            except Exception as e:
+                errors["psnr"] = f"{type(e).__name__}: {e}"
+            try:
+                eager = gpu_eager_reference(args, K, W)
+            except Exception as e:
+                errors["gpu_eager_reference"] = f"{type(e).__name__}: {e}"
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1: dist.destroy_process_group()
+        return
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True,
+               scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
+               config=dict(workload=workload_name(args.config, B, args.size, 1000, K, T), batch_per_gpu=B,
+                           global_batch=B * world, image=args.size, unet_params=model.num_params(), parallelism=f"dp{world} (batch-sharded, no collective)",
+                           l2="per-step working set (2.2 GB weights + 1.6 GB activations per image) exceeds the 126 MB L2"),
+               clocks=clk, finite=finite,
+               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / K,
+                        api="sampler.p_sample_loop(measurement=<pinned host tensor>, progress=<host callback>)"),
+               gpu_launches=K * (fl + bl + 4), roofline=roofline, configs=table)
+    if gather is not None:
+        out["final_gather"] = gather
+    if psnr is not None:
+        out["psnr_vs_reference"] = psnr
+    if eager is not None:
+        eager["speedup_of_native_b1"] = round(eager["ms_per_step"] / ms_step, 2) if B == 1 else None
+        out["gpu_eager_reference"] = eager
+    if errors:
+        out["errors"] = errors
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, steps=4, warmup=1, budget_s=60.0)
+    print(json.dumps(out))
+    if world > 1: dist.destroy_process_group()
+
+
+def dominant_roofline(args, model, dev):
+    """Roofline of the dominant kernel: the 3x3 conv 256->256 @ 256x256 (tcgen05 implicit GEMM), timed per op inside the step."""
     peaks = _peaks()
     fl, bl = model.launch_counts()
     prof = model.profile_ops(0) + model.profile_ops(1)
@@ -230,12 +440,14 @@ def run_native(args):
     roofline = dict(bound="tensor", kernel="conv_tc_persist_2sm_kernel<6,.> (3x3 256->256 @256x256 tcgen05 cta_group::2 TF32 implicit GEMM, fwd + dgrad launches)",
                     achieved=round(dom_tf, 1), peak=peaks["bf16_sustained"], unit="TFLOP/s",
                     frac=round(dom_tf / peaks["bf16_sustained"], 4), traffic=traffic,
+                    traffic_source="ncu --set full capture of this kernel (profiles/ncu_conv_traffic.json), per launch",
                     peak_source=f"{peaks['source']} bf16 sustained from MEASURED_PEAKS.json (kernel timed inside the step)",
                     dtype_note="the kernel computes in TF32 (the reference's own GPU arithmetic for conv); cuBLAS TF32 8192^3 measured "
                                "in this run the same way is the like-for-like denominator",
                     tf32_peak_measured=tf32, frac_of_tf32_sustained=round(dom_tf / tf32["tf32_tflops_sustained"], 4),
                     flops_per_launch=dom[0]["flops"], launches_averaged=len(dom), ms_per_launch=round(dom_ms, 4),
-                    all_convs_tflops=round(conv_all_tf, 1), groupnorm_kernels_gbs=round(norm_gbs, 0), hbm_peak_gbs=peaks["hbm"])
+                    all_convs_tflops=round(conv_all_tf, 1), groupnorm_kernels_gbs=round(norm_gbs, 0), hbm_peak_gbs=peaks["hbm"],
+                    step_ms_by_kind={k: round(sum(o["ms"] for o in prof if o["kind"] == k), 3) for k in sorted({o["kind"] for o in prof})})
     # secondary rooflines (informational): the HBM-bound GroupNorm apply kernel and the fused tcgen05 attention forward
     def _avg(kind, dims3):
         sel = [o for o in prof if o["kind"] == kind and o["dims"][:3] == dims3]
@@ -253,27 +465,41 @@ def run_native(args):
                                   achieved=round(a0["flops"] / ams / 1e9, 1), peak=peaks["bf16_sustained"], unit="TFLOP/s",
                                   frac=round(a0["flops"] / ams / 1e9 / peaks["bf16_sustained"], 4), ms_per_launch=round(ams, 4))
     roofline["other_kernels"] = extra
-    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True,
-               scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
-               config=dict(workload=f"{os.path.basename(args.config)}, batch {B} per GPU, {args.size}x{args.size} RGBD, 1000-step guided "
-                                    f"chain timed on {K} consecutive steps of a {T}-step respacing", batch_per_gpu=B,
-                           global_batch=B * world, image=args.size, unet_params=model.num_params(), parallelism=f"dp{world} (batch-sharded, no collective)",
-                           l2="per-step working set (2.2 GB weights + 1.6 GB activations per image) exceeds the 126 MB L2"),
-               clocks=clk, finite=finite,
-               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms / K,
-                        api="sampler.p_sample_loop(measurement=<pinned host tensor>, progress=<host callback>)"),
-               gpu_launches=K * (fl + bl + 4), roofline=roofline)
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, a, steps=1, budget_s=60.0)
-    print(json.dumps(out))
-    if world > 1: dist.destroy_process_group()
+    return roofline, fl, bl
 
 
-# ----------------------------------------------------------------------------------------------- CPU arm (oracle port)
+# ----------------------------------------------------------------------------------- the reference arms (CPU / eager CUDA)
+
+
+def _reference_chain(args, device, K, W, budget_s):
+    """Per-step times of the unmodified reference (baseline/_ref) on `device`; falls back to the oracle port (kind 'port')
+    only when the reference copy is absent."""
+    from baseline import ref_driver as rd
+    cores = os.cpu_count() or 1
+    if rd.available():
+        r = rd.time_reference_chain(args.config, device, steps=K, warmup=W, size=args.size, budget_s=budget_s,
+                                    threads=cores if device == "cpu" else None)
+        return r["step_s"], r["T"], "reference", r["finite"], cores
+    if device != "cpu":
+        raise SystemExit("baseline/_ref is missing: the eager-CUDA reference arm needs the reference copy")
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import arguments_from_file
+    a = arguments_from_file(args.config)
+    a.diffusion = dict(a.diffusion); a.diffusion["timestep_respacing"] = K + W
+    step, T, cores = cpu_step_runner(args, a)
+    idxs = list(range(T))[::-1]
+    t_begin = time.perf_counter()
+    for idx in idxs[:W]:
+        step(idx)
+    ts = []
+    for idx in idxs[W:]:
+        ts.append(step(idx))
+        if time.perf_counter() - t_begin > budget_s and len(ts) >= 2:
+            break
+    return ts, T, "port", None, cores
 
 
 def cpu_step_runner(args, a):
-    """Returns (step_fn(idx) -> seconds, T, cores): one guided step of the reference algorithm on the host CPU (oracle)."""
+    """Fallback only (no baseline/_ref): one guided step of the oracle port on the host CPU."""
     from oracle import osmosis_oracle as orc
     from osmosis_diffusion_code_b200.synthetic import synth_state_dict, synth_measurement
     cores = os.cpu_count() or 1
@@ -298,50 +524,44 @@ def cpu_step_runner(args, a):
     return step, tab.num_timesteps, cores
 
 
-def cpu_baseline(args, a, steps, budget_s):
-    step, T, cores = cpu_step_runner(args, a)
-    idx = int(0.6 * T)  # an optimised-phase step (20 phi iterations): 70 % of the chain
-    ts = []
-    t_begin = time.perf_counter()
-    for k in range(steps):
-        ts.append(step(idx - k))
-        if time.perf_counter() - t_begin > budget_s:
-            break
+def cpu_baseline(args, steps, warmup, budget_s):
+    """The reference's own CPU path on this box's host cores, a bounded sample: `warmup` + `steps` steps of the chain."""
+    ts, T, kind, finite, cores = _reference_chain(args, "cpu", steps, warmup, budget_s)
     t = statistics.median(ts)
-    return dict(value=1.0 / (1000.0 * t), unit=UNIT, cores=cores, kind="port",
-                sample=f"{len(ts)} guided step(s) (optimised-phi phase, t={idx}) of the same workload at batch 1, true fp32, "
-                       f"torch {torch.__version__} CPU kernels, {t:.2f} s/step; images/s extrapolated to 1000 steps",
-                seconds_per_step=t)
+    what = "the unmodified reference (baseline/_ref) through its own p_sample_loop" if kind == "reference" else "oracle port of the reference"
+    return dict(value=1.0 / (1000.0 * t), unit=UNIT, cores=cores, kind=kind,
+                sample=f"{len(ts)} guided steps (after {warmup} warm-up) of a {T}-step respacing of the same chain at batch 1, {what}, true "
+                       f"fp32, torch {torch.__version__} CPU kernels on {cores} threads, median {t:.2f} s/step; images/s extrapolated to "
+                       f"1000 steps", seconds_per_step=t, raw_step_seconds=[round(v, 3) for v in ts])
 
 
-def run_reference(args):
+def run_reference(args, device):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from osmosis_diffusion_code_b200.osmosis_utils.utils import arguments_from_file
-    a = arguments_from_file(args.config)
-    a.diffusion = dict(a.diffusion); a.diffusion["timestep_respacing"] = args.steps + args.warmup
-    step, T, cores = cpu_step_runner(args, a)
-    idxs = list(range(T))[::-1]
-    budget = args.cpu_budget_s
-    t_begin = time.perf_counter()
-    for idx in idxs[:min(args.warmup, 1)]:   # one untimed step warms the allocator / thread pool; more would only burn the budget
-        step(idx)
-    ts = []
-    for idx in idxs[args.warmup:]:
-        ts.append(step(idx))
-        if time.perf_counter() - t_begin > budget and len(ts) >= 2:
-            break
+    K, W = args.steps, args.warmup
+    if device == "cuda":
+        if not torch.cuda.is_available():
+            raise SystemExit("--impl reference-gpu needs a CUDA device")
+        torch.cuda.set_device(0)
+    ts, T, kind, finite, cores = _reference_chain(args, device, K, W, args.cpu_budget_s if device == "cpu" else None)
     t = sum(ts) / len(ts)
     value = 1.0 / (1000.0 * t)
-    sample = (f"{len(ts)} of the requested {args.steps} guided steps (time-capped at {budget:.0f} s), batch 1, true fp32 on {cores} host "
-              f"threads, oracle port of the reference (its Python cannot travel to the GPU box)")
-    out = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=len(ts), warmup=min(args.warmup, 1),
-               ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-               config=dict(workload=f"{os.path.basename(args.config)}, batch 1, {args.size}x{args.size} RGBD, 1000-step guided chain "
-                                    f"(extrapolated from {len(ts)} timed steps)", image=args.size),
-               cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
+    if device == "cpu":
+        what = (f"{len(ts)} of the requested {K} guided steps after {W} warm-up steps" + (f" (time-capped at {args.cpu_budget_s:.0f} s)" if len(ts) < K else "") +
+                f", batch 1, true fp32 on {cores} host threads, " +
+                ("the UNMODIFIED reference (baseline/_ref) through its own create_model / get_operator / get_conditioning_method / "
+                 "create_sampler / p_sample_loop" if kind == "reference" else "oracle port of the reference (baseline/_ref absent)"))
+    else:
+        what = (f"{len(ts)} guided steps after {W} warm-up steps, batch 1, the UNMODIFIED reference (baseline/_ref) in eager CUDA on cuda:0 "
+                f"({torch.cuda.get_device_name(0)}), cuDNN default TF32 convolutions")
+    out = dict(impl="reference" if device == "cpu" else "reference-gpu", metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=len(ts),
+               warmup=W, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f32" if device == "cpu" else "tf32 (cuDNN default)", data="synthetic",
+               config=dict(workload=workload_name(args.config, 1, args.size, 1000, K, T), batch_per_gpu=1, global_batch=1, image=args.size,
+                           note="the reference runs batch 1 only (gaussian_diffusion.py:216); under torchrun rank 0 alone runs it"),
+               cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=what), finite=finite,
                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(out))
 
@@ -351,19 +571,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=1, help="images per GPU")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--config", default=os.path.join(ROOT, "configs", "osmosis_sample_config.yaml"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-table", action="store_true", help="skip the table of the other BASELINE configurations")
+    ap.add_argument("--table-batch", type=int, default=32, help="images per GPU of the configs table (BASELINE configs 3-5)")
+    ap.add_argument("--no-eager-reference", action="store_true", help="skip the eager-CUDA reference timing and the PSNR check")
     ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed device-resident region")
-    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, "cpu")
+    elif args.impl == "reference-gpu":
+        run_reference(args, "cuda")
     else:
         run_native(args)
 

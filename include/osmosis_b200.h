@@ -177,6 +177,9 @@ typedef struct osm_guidance_params {
                             torch.optim.Adam defaults: betas 0.9 / 0.999, eps 1e-8, lr = eta per group)             */
   float* opt_state;      /* OSM_OPT_ADAM: device [B][19] = {exp_avg[9], exp_avg_sq[9], step}, zero-initialised by the
                             caller and kept across calls like the reference's optimizer object; NULL for SGD        */
+  int phi_batch;         /* rows of the caller's phi [phi_batch][9] (and opt_state) buffers: the call fails unless it equals B
+                            (0 = not stated, unchecked).  The reference builds phi with data.batch_size rows
+                            (measurements.py:225-232) independently of the batch it is later run on                  */
 } osm_guidance_params;
 
 /* replaces Operator.forward (measurements.py:138-151, 251-264, 363-376): out[B,3,HW] = A_phi(x[B,4,HW]).

@@ -91,8 +91,12 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
     def kernel_params(self):
         if self._params is None:
             op = self.operator
+            kind = getattr(op, "kind_name", None)
+            if kind not in OP_KIND:
+                raise NotImplementedError(f"the native `osmosis` conditioning has guidance kernels for the operators {sorted(OP_KIND)}; "
+                                          f"{type(op).__name__} (kind {kind!r}) is not one of them")
             p = _lib.GuidanceParamsC()
-            p.op_kind = OP_KIND[op.kind_name]
+            p.op_kind = OP_KIND[kind]
             p.depth_kind = op.depth_kind
             for i in range(3):
                 p.depth_val[i] = op.depth_val[i]
@@ -116,6 +120,7 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
             p.loss_kind = 1 if self.loss_function == "mse" else 0
             p.optimizer = 1 if str(op.optimizer).lower() == "adam" else 0
             p.opt_state = op.opt_state.data_ptr() if op.opt_state is not None else None
+            p.phi_batch = int(op.phi.shape[0])
             self._params = p
         return self._params
 
@@ -133,8 +138,17 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
         s = self.scale.float()
         return (s.repeat(channels) if s.numel() == 1 else s).contiguous()
 
+    def check_batch(self, x):
+        """The operator's phi / optimizer state hold one row per image (`batch_size` of get_operator, which the reference takes
+        from data.batch_size = 1 in every shipped YAML): a batch of another size would index them out of bounds."""
+        n = int(self.operator.phi.shape[0])
+        if int(x.shape[0]) != n:
+            raise ValueError(f"the operator was built for batch_size={n} but the sampler runs {int(x.shape[0])} images: pass "
+                             f"batch_size={int(x.shape[0])} to get_operator")
+
     def guidance_gradient(self, x_0_hat, measurement, freeze_flag_dev, g_x0, losses):
         """One launch: phi loop + d(total loss)/d(x_0_hat).  All arguments are device tensors."""
+        self.check_batch(x_0_hat)
         B, Cc, H, W = x_0_hat.shape
         L = _lib.load()
         _lib.check(L.osm_guidance_phi_loop(C.byref(self.kernel_params()), _lib.ptr(x_0_hat), _lib.ptr(measurement),
@@ -144,6 +158,7 @@ class PosteriorSamplingOsmosis(ConditioningMethod):
     # ---- the reference-facing call (autograd-compatible path) ------------------------------------------
     def conditioning(self, x_prev, x_t, x_0_hat, measurement, **kwargs):
         freeze_phi = kwargs.get("freeze_phi", False)
+        self.check_batch(x_t)
         buf = self._buffers(x_t)
         self.operator.set_variable_gradients(value=not freeze_phi)
         buf["freeze"].fill_(1 if freeze_phi else 0)

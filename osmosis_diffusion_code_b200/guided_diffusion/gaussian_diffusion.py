@@ -210,6 +210,8 @@ class GaussianDiffusion:
         B, Cc, H, W = x.shape
         dev = x.device
         f32 = dict(dtype=torch.float32, device=dev)
+        if hasattr(cond, "check_batch"):
+            cond.check_batch(x)
         return dict(
             coef=self.mean_processor.table.on(dev), t_idx=torch.zeros(B, dtype=torch.int32, device=dev),
             t_model=torch.zeros(B, **f32), freeze=torch.zeros(1, dtype=torch.int32, device=dev),
@@ -303,9 +305,9 @@ class GaussianDiffusion:
             stepper.step(idx)
             if progress is not None:
                 progress(idx, st["ps_loss"].cpu().numpy())
-        self.last_loss = st["ps_loss"]
-        self.last_gradients = st["grad"]
-        self.last_pred_xstart = st["x0"]
+        self.last_loss = st["ps_loss"].clone()
+        self.last_gradients = st["grad"].clone()
+        self.last_pred_xstart = st["x0"].clone()
         return stepper.img.clone()
 
     def _loop_autograd_ps(self, model, measurement_cond_fn, x_start, measurement, idxs):
@@ -364,8 +366,8 @@ class GaussianDiffusion:
             self.last_record = self._finish_record(record)
         variable_dict = cond.operator.optimize(freeze_phi=True)
         loss = st["losses"][:, 0].cpu().numpy()
-        self.last_gradients = st["grad"]
-        self.last_aux = st["losses"]
+        self.last_gradients = st["grad"].clone()    # the stepper (and its buffers) is reused by the next p_sample_loop call
+        self.last_aux = st["losses"].clone()
         return img.clone(), variable_dict, loss, st["x0"].detach().cpu()
 
     def _stepper_for(self, model, cond, x_start, measurement, sample_pattern, noise_mode, cuda_graph):
@@ -458,6 +460,17 @@ class FusedStepper:
         self.graph_unguided = None
         self.calls = 0
         self.calls_unguided = 0
+        self.bind_gen = None
+
+    def _check_plan(self):
+        """The captured graphs hold raw pointers into the UNet engine's bound workspace.  `UNetModel._ensure_bound` frees and
+        re-plans it whenever another (B, H, W) runs through the same model, so graphs captured under an older plan are
+        dropped here (the next step runs eagerly, which re-binds, and the one after re-captures)."""
+        m = self.model
+        if self.bind_gen is not None and (m._bind_generation != self.bind_gen or m._bound != (self.img.shape[0],) + tuple(self.img.shape[2:])):
+            self.graph = self.graph_unguided = None
+            self.calls = self.calls_unguided = 0
+        self.bind_gen = None
 
     def _draw_into(self, buf):
         if self.noise_mode == "shared":
@@ -466,6 +479,14 @@ class FusedStepper:
             buf.normal_()
 
     def step(self, idx, freeze=None):
+        s, st, T = self.sampler, self.st, self.sampler.num_timesteps
+        self._check_plan()
+        try:
+            self._step(idx, freeze)
+        finally:
+            self.bind_gen = self.model._bind_generation
+
+    def _step(self, idx, freeze=None):
         s, st, T = self.sampler, self.st, self.sampler.num_timesteps
         if self.ps:
             st["t_idx"].fill_(idx)

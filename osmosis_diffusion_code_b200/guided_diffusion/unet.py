@@ -54,6 +54,7 @@ def create_model(image_size, num_channels, num_res_blocks, channel_mult="", lear
                       num_heads=num_heads, num_head_channels=num_head_channels, num_heads_upsample=num_heads_upsample,
                       use_scale_shift_norm=use_scale_shift_norm, resblock_updown=resblock_updown,
                       use_new_attention_order=use_new_attention_order, conv_mode=conv_mode)
+    model._surgery = pretrain_model == "osmosis"
     try:
         model.load_state_dict(torch.load(model_path, map_location="cpu"))
     except Exception as e:  # same policy as the reference: report and continue with the random init
@@ -124,6 +125,8 @@ class UNetModel:
         self._bound = None       # (B, H, W)
         self._ws = None
         self._generation = 0
+        self._surgery = False    # set by create_model for pretrain_model == "osmosis" (change_input_output_unet)
+        self._bind_generation = 0   # bumped whenever the workspace is re-planned: captured CUDA graphs of older plans are stale
 
     # ---- parameters -------------------------------------------------------------------------------
     def param_specs(self):
@@ -137,14 +140,17 @@ class UNetModel:
         uniform(+-1/sqrt(fan_in)) convs / linears, unit GroupNorm, and zeros where it applies zero_module."""
         g = torch.Generator().manual_seed(0)
         sd = {}
+        shapes = dict(self._specs)
         for name, shape in self._specs:
-            leaf = name.rsplit(".", 1)[-1]
+            stem, leaf = name.rsplit(".", 1)
+            # the osmosis 4-in / 8-out surgery (utils.py:279, :286) replaces out[-1] by a FRESH nn.Conv2d: default init, not zero
+            zeroed = ".out_layers.3." in name or ".proj_out." in name or (name.startswith("out.2.") and not self._surgery)
             if ".in_layers.0." in name or ".out_layers.0." in name or ".norm." in name or name.startswith("out.0."):
                 t = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
-            elif ".out_layers.3." in name or ".proj_out." in name or name.startswith("out.2."):
+            elif zeroed:
                 t = torch.zeros(shape)
-            else:
-                fan_in = math.prod(shape[1:]) if leaf == "weight" else shape[0]
+            else:   # nn.Conv2d / nn.Linear default: U(+-1/sqrt(fan_in)) for the weight and the bias (fan_in of the weight)
+                fan_in = math.prod(shapes.get(stem + ".weight", shape)[1:])
                 t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
             sd[name] = t
         return sd
@@ -224,6 +230,7 @@ class UNetModel:
         with torch.cuda.device(self.device):
             _lib.check(self._L.osm_unet_bind(self._h, B, H, W, C.c_void_p(base), nbytes))
         self._bound = (B, H, W)
+        self._bind_generation += 1
 
     def workspace_bytes(self, B, H, W):
         return int(self._L.osm_unet_workspace_bytes(self._h, B, H, W))

@@ -144,7 +144,8 @@ class ShardedImageLoader:
         self.ds, self.b, self.rank, self.world, self.device, self.degamma = dataset, batch_per_rank, rank, world, device, degamma
         self.size = size
         n = len(dataset) if stop_after is None or stop_after < 0 else min(len(dataset), stop_after)
-        self.indices = list(range(rank, n, world))
+        from ..sharding import shard_indices
+        self.indices = shard_indices(n, rank, world)
 
     def __len__(self):
         return (len(self.indices) + self.b - 1) // self.b

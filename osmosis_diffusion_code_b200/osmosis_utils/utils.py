@@ -184,6 +184,8 @@ def postprocess_samples(operator, pred_xstart, measurement):
     if not y.is_cuda:
         raise _lib.OsmError("post-processing runs on CUDA tensors only (no CPU fallback)")
     B, _, H, W = x0.shape
+    if int(operator.phi.shape[0]) != B or int(y.shape[0]) != B:
+        raise ValueError(f"postprocess_samples: {B} samples, {int(y.shape[0])} measurements, phi for {int(operator.phi.shape[0])} images")
     rgb = torch.empty(B, 3, H, W, dtype=torch.float32, device=y.device)
     deg, rec = torch.empty_like(rgb), torch.empty_like(rgb)
     norm = torch.empty(B, dtype=torch.float32, device=y.device)

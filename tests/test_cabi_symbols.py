@@ -25,7 +25,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_error_string():
     lib = L_.load()
-    assert lib.osm_abi_version() == 2
+    assert lib.osm_abi_version() == 3
     assert lib.osm_unet_create(None, None) != 0
     assert b"null" in lib.osm_last_error_string()
 

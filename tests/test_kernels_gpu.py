@@ -234,6 +234,51 @@ def test_attention_forward_backward(B, L, Cc, heads):
     assert rel_err(gq.permute(0, 2, 1).cpu(), gref) < 5e-5
 
 
+FLASH_TOL = 3e-3     # single-pass TF32 on tcgen05 (10 mantissa bits on Q, K, V, P) against the fp32 oracle
+
+
+@pytest.mark.parametrize("B,L,Cc,heads", [(1, 1024, 512, 8), (2, 256, 1024, 16), (3, 64, 1024, 16), (8, 1024, 512, 8), (1, 64, 1024, 16)])
+def test_flash_attention_forward_backward(B, L, Cc, heads):
+    """The PRODUCT attention path: flash_fwd_kernel / flash_dq_kernel / flash_dkv_kernel (tcgen05 kind::tf32, TMEM
+    accumulators) + tok_to_chan_kernel, through osm_dbg_attention_flash[_bwd], against the oracle's QKVAttentionLegacy
+    (unet.py:416-433) and autograd at the three (L, heads) shapes of the shipped UNet: 32x32 / 8 heads, 16x16 and 8x8 /
+    16 heads.  Output, the three gradient thirds (dq, dk, dv) and the log2-domain LSE the backward consumes."""
+    g = torch.Generator().manual_seed(L + Cc + B)
+    qkv = (torch.randn(B, 3 * Cc, L, generator=g) * 1.2).requires_grad_(True)      # logits of std ~1.4: a peaked softmax
+    ref = orc.qkv_attention_legacy(qkv, heads)                                    # [B, C, L]
+    go = torch.randn(B, Cc, L, generator=g)
+    gref = torch.autograd.grad(ref, qkv, go)[0]
+    qd = qkv.detach().permute(0, 2, 1).contiguous().to(DEV)                       # [B, L, 3C] token-major, heads as (q,k,v) x 64
+    god = go.permute(0, 2, 1).contiguous().to(DEV)
+    qkvT = torch.zeros(B, 3 * Cc, L, device=DEV)
+    out = torch.zeros(B, L, Cc, device=DEV)
+    lse = torch.zeros(B, heads, L, device=DEV)
+    Dv = torch.zeros(B, heads, L, device=DEV)
+    goT = torch.zeros(B, Cc, L, device=DEV)
+    gq = torch.zeros(B, L, 3 * Cc, device=DEV)
+    st = L_.stream()
+    L_.check(lib().osm_dbg_attention_flash(L_.ptr(qd), L_.ptr(qkvT), L_.ptr(out), L_.ptr(lse), B, L, Cc, heads, st))
+    L_.check(lib().osm_dbg_attention_flash_bwd(L_.ptr(qd), L_.ptr(qkvT), L_.ptr(out), L_.ptr(lse), L_.ptr(Dv), L_.ptr(god), L_.ptr(goT),
+                                               L_.ptr(gq), B, L, Cc, heads, st))
+    torch.cuda.synchronize()
+    assert rel_err(out.permute(0, 2, 1).cpu(), ref.detach()) < FLASH_TOL
+    got = gq.permute(0, 2, 1).cpu().view(B, heads, 3, 64, L)
+    want = gref.view(B, heads, 3, 64, L)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        assert rel_err(got[:, :, i], want[:, :, i]) < 2 * FLASH_TOL, name
+    x = qkv.detach().double().view(B, heads, 3, 64, L)
+    s = torch.einsum("bhct,bhcs->bhts", x[:, :, 0], x[:, :, 1]) / 8.0
+    lse_ref = torch.logsumexp(s, dim=-1) / math.log(2.0)
+    assert maxdiff(lse.cpu(), lse_ref) < 1e-2
+    # bit-reproducible: one owner per output row, no atomics
+    out2, gq2 = torch.zeros_like(out), torch.zeros_like(gq)
+    L_.check(lib().osm_dbg_attention_flash(L_.ptr(qd), L_.ptr(qkvT), L_.ptr(out2), L_.ptr(lse), B, L, Cc, heads, st))
+    L_.check(lib().osm_dbg_attention_flash_bwd(L_.ptr(qd), L_.ptr(qkvT), L_.ptr(out2), L_.ptr(lse), L_.ptr(Dv), L_.ptr(god), L_.ptr(goT),
+                                               L_.ptr(gq2), B, L, Cc, heads, st))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and torch.equal(gq, gq2)
+
+
 @pytest.mark.parametrize("cout,silu,mod", [(256, 1, True), (512, 0, False), (128, 1, False)])
 def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
     """GroupNorm statistics reduced in the tcgen05 conv's epilogue (conv_epilogue.cuh) + the finalize kernel, checked

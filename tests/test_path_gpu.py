@@ -449,3 +449,68 @@ def test_uncond_inverse_vs_reference_golden(tmp_path, monkeypatch):
     assert maxdiff(rgb.cpu(), gold["x_start_rgb"]) < 1e-4
     assert maxdiff(depth[0:1].cpu(), gold["x_depth_pmm"]) < 5e-4
     assert os.path.exists(os.path.join(str(tmp_path), "image_0_process.png"))
+
+
+def test_stepper_graph_is_dropped_when_the_model_is_rebound():
+    """A cached FusedStepper's CUDA graph holds pointers into the engine's bound workspace; running another batch shape
+    through the same model re-plans (and frees) it.  The stepper must notice (UNetModel._bind_generation) and re-capture
+    instead of replaying the stale plan: results equal those of an undisturbed stepper bit for bit."""
+    from osmosis_diffusion_code_b200.guided_diffusion.gaussian_diffusion import FusedStepper
+    cname = "osmosis"
+    y, _ = case_inputs("meas:" + cname)
+    m = model("fp32")
+    g = torch.Generator().manual_seed(31)
+    x_T = torch.randn(1, 4, *y.shape[2:], generator=g)
+    T = 6
+    noises = [torch.randn(1, 4, *y.shape[2:], generator=g) for _ in range(T)]
+
+    def chain(disturb):
+        cfg, op, cond, sampler = _native_objects(cname, 1)
+        img = x_T.to(DEV).clone()
+        stepper = FusedStepper(sampler, m, cond, img, y.to(DEV), cfg["sample_pattern"], cuda_graph=True)
+        for k, idx in enumerate(range(sampler.num_timesteps)[::-1][:T]):
+            if disturb and k == 3:     # graph captured at k == 1; now another (B, H, W) goes through the same model
+                gen = m._bind_generation
+                m._forward_raw(torch.randn(2, 4, 16, 16, device=DEV), torch.full((2,), 10.0, device=DEV))
+                assert m._bind_generation == gen + 1
+            stepper._draw_into = lambda buf, _k=k: buf.copy_(noises[_k].to(DEV)) if buf.shape[1] == 4 else buf.zero_()
+            stepper.step(idx)
+        torch.cuda.synchronize()
+        return img.clone(), op.phi.clone(), stepper
+
+    a_img, a_phi, _ = chain(False)
+    b_img, b_phi, st = chain(True)
+    assert st.graph is not None                       # re-captured after the disturbance
+    assert torch.equal(a_img, b_img) and torch.equal(a_phi, b_phi)
+
+
+def test_batch_mismatch_and_unknown_operator_raise():
+    """phi / optimizer state hold one row per image (`batch_size` of get_operator): running another batch size must fail
+    loudly instead of indexing out of bounds - on the host (ValueError) and in the C ABI (phi_batch != B).  An operator
+    the guidance kernel does not know raises NotImplementedError instead of a KeyError."""
+    cname = "osmosis"
+    cfg, op, cond, sampler = _native_objects(cname, 1)
+    y, _ = case_inputs("meas:" + cname)
+    x2 = torch.randn(2, 4, *y.shape[2:], device=DEV)
+    y2 = y.to(DEV).repeat(2, 1, 1, 1)
+    with pytest.raises(ValueError):
+        sampler.fused_state(model("fp32"), cond, x2, y2)
+    with pytest.raises(ValueError):
+        cond.conditioning(x_prev=x2, x_t=x2.clone(), x_0_hat=x2.clone(), measurement=y2, freeze_phi=True)
+    from osmosis_diffusion_code_b200.osmosis_utils.utils import postprocess_samples
+    with pytest.raises(ValueError):
+        postprocess_samples(op, x2, y2)
+    p = cond.kernel_params()
+    assert p.phi_batch == 1
+    buf = dict(f=torch.zeros(1, dtype=torch.int32, device=DEV), g=torch.empty_like(x2), l=torch.zeros(2, 4, device=DEV))
+    rc = lib().osm_guidance_phi_loop(C.byref(p), L_.ptr(x2), L_.ptr(y2), L_.ptr(op.phi), L_.ptr(buf["f"]), L_.ptr(buf["g"]), L_.ptr(buf["l"]),
+                                     2, x2.shape[2] * x2.shape[3], L_.stream())
+    assert rc != 0 and b"phi_batch" in lib().osm_last_error_string()
+
+    class Foreign:
+        kind_name = "my_new_operator"
+        phi = op.phi
+    cond2 = get_conditioning_method(cfg["conditioning"]["method"], Foreign(), get_noise(**cfg["measurement"]["noise"]),
+                                    **cfg["conditioning"]["params"], **cfg["sample_pattern"], **cfg["aux_loss"])
+    with pytest.raises(NotImplementedError):
+        cond2.kernel_params()

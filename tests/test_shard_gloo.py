@@ -7,25 +7,31 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from osmosis_diffusion_code_b200.sharding import shard_range, gather_images, max_over_ranks
+from osmosis_diffusion_code_b200.sharding import shard_indices, gather_images, max_over_ranks
 
 
-def test_shard_range_partitions_exactly():
+def test_shard_indices_partition_exactly_and_match_the_loader():
+    from osmosis_diffusion_code_b200.osmosis_utils.data import ShardedImageLoader
+
+    class DS:
+        def __init__(self, n): self.n = n
+        def __len__(self): return self.n
     for n in (1, 2, 7, 32, 255, 256):
         for world in (1, 2, 3, 4, 8):
-            spans = [shard_range(n, r, world) for r in range(world)]
-            assert spans[0][0] == 0 and spans[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-            sizes = [hi - lo for lo, hi in spans]
+            parts = [shard_indices(n, r, world) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            sizes = [len(p) for p in parts]
             assert max(sizes) - min(sizes) <= 1
+            for r in range(world):   # the same partition as the input loader (image i -> rank i mod world)
+                assert ShardedImageLoader(DS(n), 4, rank=r, world=world).indices == parts[r]
 
 
 def _worker(rank, world, port, n_images, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = shard_range(n_images, rank, world)
-    local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 2, 3).contiguous() * 10.0
+    idx = shard_indices(n_images, rank, world)
+    local = torch.tensor(idx, dtype=torch.float32)[:, None, None].expand(len(idx), 2, 3).contiguous() * 10.0
     full = gather_images(local, n_images)
     t = max_over_ranks(1.0 + rank)
     q.put((rank, full[:, 0, 0].tolist(), t))
