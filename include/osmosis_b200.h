@@ -64,7 +64,8 @@ int osm_unet_param_info(osm_unet_t h, int index, const char** name, int* ndim, i
  * replaces model.load_state_dict (unet.py:94-97).                                                    */
 int osm_unet_load_param(osm_unet_t h, const char* name, const float* host_data, int64_t numel, void* stream);
 /* Bytes of caller-provided device workspace needed for batch B at HxW (activations kept for the input
- * VJP, gradients, scratch).                                                                          */
+ * VJP, gradients, scratch).  Plans the engine for that shape: an existing binding is dropped and
+ * osm_unet_bind must be called again before the next forward.                                         */
 int64_t osm_unet_workspace_bytes(osm_unet_t h, int B, int H, int W);
 /* Builds the launch plan (buffer offsets, TMA descriptors) for (B,H,W) on `workspace`.               */
 int osm_unet_bind(osm_unet_t h, int B, int H, int W, void* workspace, int64_t workspace_bytes);

@@ -8,7 +8,8 @@ through the small golden UNet.
 Tolerances (normalised max error = max|a-b| / max|b| unless stated), per level:
   * UNet output / input-VJP vs the fp32 CPU oracle:        exact mode 2e-4 / 1e-3,  product mode (TF32 tensor cores) 1e-2 / 3e-2
   * guided step (teacher-forced: the oracle's x_t, phi, noise), vs the oracle and vs the reference on CUDA:
-      pred_xstart 1e-3 exact / 2e-2 product (x the conditioning 1/sqrt(abar) of the step), loss 1e-3 / 2e-2,
+      pred_xstart 1e-4 exact / 1e-2 product TIMES the step's amplification sqrt(1/abar_t - 1) max|x_t| / max|x0| (x0 = sqrt(1/abar) x -
+      sqrt(1/abar - 1) eps magnifies the UNet's rounding: 38x at t = 850), loss 1e-3 / 2e-2,
       x_{t-1}: every pixel within the clamp bound 2 * scale * clip, >= 99 % (exact) / 97 % (product) of pixels within 1e-3 / 2e-2,
       phi 5e-6 exact / 5e-5 product (absolute)
   * RNG stream: the loop's draws are BIT-identical to the reference's (`randn_like` of [1,3,H,W] then [1,4,H,W] per step on the device).
@@ -134,7 +135,11 @@ def _native_step(mode, cfg_name, idx, x, noise, y):
                 phi={n: getattr(op, n).detach().cpu().reshape(-1) for n in op.groups}, cond=cond, freeze=freeze)
 
 
-def _check_step(tag, got, want_x_next, want_x0, want_loss, want_phi, exact, cond):
+def _amp(tab, idx, x, want_x0):
+    return max(1.0, float(tab.sqrt_recipm1_alphas_cumprod[idx]) * float(x.abs().max()) / float(want_x0.abs().max()))
+
+
+def _check_step(tag, got, want_x_next, want_x0, want_loss, want_phi, exact, cond, amp):
     bound = 2 * float(cond.scale.max()) * cond.gradient_clip_value * 1.01
     scale = max(1.0, float(want_x_next.abs().max()))
     d = (got["x_next"] - want_x_next).abs()
@@ -142,9 +147,9 @@ def _check_step(tag, got, want_x_next, want_x0, want_loss, want_phi, exact, cond
     frac = float((d < tight).float().mean())
     e_x0, e_loss = rel_err(got["x0"], want_x0), rel_err(got["loss"], want_loss)
     e_phi = max(maxdiff(got["phi"][n], want_phi[n].reshape(-1)) for n in got["phi"])
-    print(f"{tag}: x0 {e_x0:.2e}  loss {e_loss:.2e}  x_next max {float(d.max()):.2e} (clamp bound {bound:.3f}), within {tight:.0e}: {frac:.4f}  "
+    print(f"{tag}: x0 {e_x0:.2e} (amplification {amp:.1f})  loss {e_loss:.2e}  x_next max {float(d.max()):.2e} (clamp bound {bound:.3f}), within {tight:.0e}: {frac:.4f}  "
           f"phi {e_phi:.2e}")
-    assert e_x0 < (1e-3 if exact else 2e-2), tag
+    assert e_x0 < (1e-4 if exact else 1e-2) * amp, tag
     assert e_loss < (1e-3 if exact else 2e-2), tag
     assert float(d.max()) <= bound + tight, tag
     assert frac > (0.99 if exact else 0.97), tag
@@ -166,7 +171,7 @@ def test_teacher_forced_guided_steps_vs_oracle_at_full_size(cfg_name):
             got = _native_step(mode, cfg_name, idx, x, noise, y)
             assert got["freeze"] == orc.is_freeze_phi(gspec, idx, tab.num_timesteps)
             _check_step(f"{cfg_name} t={idx} [{mode}] vs oracle", got, r["x_next"], r["pred_xstart"], r["loss"], want_phi, mode == "fp32",
-                        got["cond"])
+                        got["cond"], _amp(tab, idx, x, r["pred_xstart"]))
 
 
 @needs_ref
@@ -202,7 +207,7 @@ def test_teacher_forced_guided_steps_vs_reference_on_cuda(cfg_name):
                 assert set(want_phi) == set(got["phi"])
                 # against cuDNN-TF32 both sides carry TF32 rounding: same bars as product-vs-oracle
                 _check_step(f"{cfg_name} t={idx} [{mode}] vs reference on CUDA (cudnn tf32={tf32})", got, x_next_ref, x0_ref.cpu(),
-                            torch.as_tensor(loss), want_phi, mode == "fp32", got["cond"])
+                            torch.as_tensor(loss), want_phi, mode == "fp32", got["cond"], _amp(tab, idx, x, x0_ref.cpu()))
                 assert maxdiff(got["logvar"], logvar_ref.cpu()) < (1e-4 if mode == "fp32" else 2e-2)
     finally:
         torch.backends.cudnn.allow_tf32 = old
