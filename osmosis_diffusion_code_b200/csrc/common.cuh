@@ -97,7 +97,7 @@ struct ConvArgs {
   int stat_mode, stat_cpg; float* stat_partial; const float* stat_x; int stat_ldx; const void* stat_coef; int stat_silu;
   // halo kernel (3x3, conv_tc_halo_2sm_kernel): halo = 0 off, 10 / 16 = shared-memory row pitch of the halo tile (10 = one
   // dense TMA box per K block).  xf_coef != null: the A operand is tf32(SiLU?(x a + b)) computed in shared memory from the
-  // raw input x, with (a, b) = xf_coef[b][ci].xy (float4 per (image, input channel), as written by gn_coef_kernel).
+  // raw input x, with (a, b) = xf_coef[b][ci] (float2 per (image, input channel), as written by gn_coef_fwd_kernel).
   int halo, halo_bo; const void* xf_coef; int xf_silu;
 };
 bool conv_tc_halo_ok(int B, int H, int W, int Cin_p, int Cout_p, int taps);   // shapes the halo kernel takes
@@ -156,6 +156,8 @@ int gn_bwd_apply_launch(const GnBwdArgs& a, cudaStream_t s);   // apply only: bs
 int gn_fused_finalize_launch(const float* partial, int slots_per_image, const float* fwd_stats, float* out, int B, int HW, int C,
                              int mode, cudaStream_t s);
 int gn_coef_launch(const GnArgs& a, float* coef /*[B][C][4]*/, cudaStream_t s);
+// forward operand-transform coefficients of GroupNorm(+modulation) `a`: coef[b][c] = (A, Bc) with pre-activation = x A + Bc
+int gn_coef_fwd_launch(const GnArgs& a, float* coef /*[B][C][2]*/, cudaStream_t s);
 
 // ---------------- attention (QKVAttentionLegacy, fp32) ----------------
 // qkv [B,L,3C] token-major, head h owns channels [h*3*ch, (h+1)*3*ch) as (q,k,v); out [B,L,C]

@@ -372,3 +372,59 @@ def test_conv_cta_pair_kernel(case, monkeypatch):
     gx = torch.full((B, H, W, cin_p), float("nan"), device=DEV)
     run_conv(0, gyp, cout_p, wd, None, None, 0, 0, gx, cin_p, 0, B, H, W, cout_p, cin_p, taps)      # dgrad: Cin_p may be < 256
     assert rel_err(nchw(gx)[:, :cin], gref) < TF32_TOL
+
+
+HALO_CASES = [
+    # B, H, W, Cin, Cout, modulation, residual
+    (1, 32, 32, 64, 256, False, False),
+    (2, 16, 24, 96, 256, True, True),      # 3 x 1 x 2 = 6 tiles
+    (3, 16, 8, 32, 512, True, False),      # 3 tiles: an odd count leaves the last pair half empty; two N tiles
+    (1, 64, 64, 256, 256, True, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,mod,res", HALO_CASES)
+def test_conv_halo_fused_groupnorm_silu(B, H, W, cin, cout, mod, res):
+    """The halo-tile CTA-pair tcgen05 conv with GroupNorm32 + scale-shift + SiLU applied to its operand in shared memory
+    (conv_tc_halo_2sm_kernel, XFORM) against torch: conv2d(SiLU(group_norm(x) (1 + scale) + shift)) (+ residual)
+    (nn.py:17-19, unet.py:315-335).  The statistics come from torch, so the test isolates the coefficient kernel, the halo
+    geometry (zero padding applied AFTER the activation), the in-place transform and the tap-shifted descriptors.
+    The same kernel without the transform is checked against the plain conv."""
+    g = torch.Generator().manual_seed(H * W + cin)
+    x = torch.randn(B, cin, H, W, generator=g) * 1.5 + 0.3
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    bias = torch.randn(cout, generator=g)
+    gamma, beta = 1 + 0.2 * torch.randn(cin, generator=g), 0.2 * torch.randn(cin, generator=g)
+    ss = 0.3 * torch.randn(B, 2 * cin + 8, generator=g) if mod else None
+    resid = torch.randn(B, cout, H, W, generator=g) if res else None
+    y = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    if mod:
+        y = y * (1 + ss[:, :cin, None, None]) + ss[:, cin:2 * cin, None, None]
+    want = F.conv2d(F.silu(y).double(), w.double(), bias.double(), padding=1).float() + (resid if res else 0.0)
+    xg = x.view(B, 32, -1)
+    stats = torch.stack([xg.mean(-1), 1.0 / torch.sqrt(xg.var(-1, unbiased=False) + 1e-5)], -1).contiguous().to(DEV)
+    xd = nhwc(x)
+    wf, _, cout_p, cin_p = pack_weight(w, 9, round_tf32=True)
+    assert (cout_p, cin_p) == (cout, cin)
+    coef = torch.empty(B, cin, 2, device=DEV)
+    # coefficients through the engine's kernel: reuse the GroupNorm debug entry? it has none -> compute (a, b) as gn_coef_fwd_kernel does
+    cpg = cin // 32
+    mean = stats[:, :, 0].repeat_interleave(cpg, 1); rstd = stats[:, :, 1].repeat_interleave(cpg, 1)
+    sc1 = (1 + ss[:, :cin]).to(DEV) if mod else torch.ones(B, cin, device=DEV)
+    sh = ss[:, cin:2 * cin].to(DEV) if mod else torch.zeros(B, cin, device=DEV)
+    ga, be = gamma.to(DEV), beta.to(DEV)
+    coef[..., 0] = rstd * ga * sc1
+    coef[..., 1] = (be - mean * rstd * ga) * sc1 + sh
+    out = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    bd = bias.to(DEV)
+    rd_ = nhwc(resid) if res else None
+    L_.check(lib().osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), L_.ptr(coef), 1, L_.ptr(rd_), cout if res else 0, 1 if res else 0,
+                                     L_.ptr(out), cout, B, H, W, cin, cout, 10, 0, L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out), want) < TF32_TOL
+    # no transform: the plain conv of x
+    out2 = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    L_.check(lib().osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), None, 0, None, 0, 0, L_.ptr(out2), cout, B, H, W, cin, cout, 10, 0,
+                                     L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out2), F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()) < TF32_TOL

@@ -514,3 +514,28 @@ def test_batch_mismatch_and_unknown_operator_raise():
                                     **cfg["conditioning"]["params"], **cfg["sample_pattern"], **cfg["aux_loss"])
     with pytest.raises(NotImplementedError):
         cond2.kernel_params()
+
+
+def test_unet_with_groupnorm_fused_into_the_conv_operand_vs_reference_golden(monkeypatch):
+    """OSM_GN_XFORM=2 forces the halo conv kernel with the in-shared-memory GroupNorm + SiLU transform onto every 3x3 conv
+    whose shape allows it (here: all non-resampling ResBlock convs of the small golden UNet; at full size the planner
+    picks it for the 256x256 and 128x128 levels, which tests/test_fullsize_parity_gpu.py covers).  Output and input-VJP
+    against the unmodified reference's golden, product-mode tolerance; and the launch count drops (no apply passes)."""
+    gold = golden()
+    x, t, cot = case_inputs("unet")
+    base = model("tc")
+    base._forward_raw(x.to(DEV), t.to(DEV).float())
+    n_base = base.launch_counts()[0]
+    monkeypatch.setenv("OSM_GN_XFORM", "2")
+    m = _model("tc")
+    xd = x.to(DEV).requires_grad_(True)
+    out = m(xd, t.to(DEV))
+    (gx,) = torch.autograd.grad(out, xd, cot.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu(), gold["unet_out"]) < 1e-2
+    assert rel_err(gx.cpu(), gold["unet_gx"]) < 1e-2
+    kinds = [o["kind"] for o in m.profile_ops(0)]
+    kinds_base = [o["kind"] for o in base.profile_ops(0)]
+    assert kinds.count("gn_apply") < kinds_base.count("gn_apply")
+    print("forward launches with / without the fused operand transform:", m.launch_counts()[0], n_base,
+          "gn_apply ops", kinds.count("gn_apply"), "vs", kinds_base.count("gn_apply"))
