@@ -238,11 +238,9 @@ int osm_dbg_conv_stats(const float* x, int ldx, const float* w_packed, const flo
                        float* scratch_partial, float* scratch_coef, float* stats_out, int* fused, void* stream);
 /* Halo-tile CTA-pair tcgen05 conv (3x3, Cout % 256 == 0, H % 16 == 0, W % 8 == 0).  coef != NULL: [B][Cin] float2 (a, b) and the
  * conv runs on tf32(SiLU?(x a + b)) computed in shared memory from the raw x (GroupNorm + SiLU fused into the operand load,
- * nn.py:17-19 + unet.py:315-335).  pitch 10 / 16 and base_offset 0 / 1 select the shared-memory layout variants.  stats_mode 1 also
- * reduces the GroupNorm statistics of the output (as osm_dbg_conv_stats). */
+ * nn.py:17-19 + unet.py:315-335).  tile_n: 128 / 256 = output channels per CTA-pair tile, 0 = chosen by the plan. */
 int osm_dbg_conv_halo(const float* x, int ldx, const float* w_packed, const float* bias, const float* coef, int silu, const float* res,
-                      int ldr, int res_mode, float* out, int ldo, int B, int H, int W, int Cin, int Cout, int pitch, int base_offset,
-                      void* stream);
+                      int ldr, int res_mode, float* out, int ldo, int B, int H, int W, int Cin, int Cout, int tile_n, void* stream);
 int osm_dbg_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p,
                              int taps, int round_tf32, void* stream);
 int osm_dbg_gn_forward(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,

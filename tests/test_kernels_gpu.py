@@ -383,8 +383,9 @@ HALO_CASES = [
 ]
 
 
+@pytest.mark.parametrize("tile_n", [256, 128])
 @pytest.mark.parametrize("B,H,W,cin,cout,mod,res", HALO_CASES)
-def test_conv_halo_fused_groupnorm_silu(B, H, W, cin, cout, mod, res):
+def test_conv_halo_fused_groupnorm_silu(B, H, W, cin, cout, mod, res, tile_n):
     """The halo-tile CTA-pair tcgen05 conv with GroupNorm32 + scale-shift + SiLU applied to its operand in shared memory
     (conv_tc_halo_2sm_kernel, XFORM) against torch: conv2d(SiLU(group_norm(x) (1 + scale) + shift)) (+ residual)
     (nn.py:17-19, unet.py:315-335).  The statistics come from torch, so the test isolates the coefficient kernel, the halo
@@ -419,12 +420,12 @@ def test_conv_halo_fused_groupnorm_silu(B, H, W, cin, cout, mod, res):
     bd = bias.to(DEV)
     rd_ = nhwc(resid) if res else None
     L_.check(lib().osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), L_.ptr(coef), 1, L_.ptr(rd_), cout if res else 0, 1 if res else 0,
-                                     L_.ptr(out), cout, B, H, W, cin, cout, 10, 0, L_.stream()))
+                                     L_.ptr(out), cout, B, H, W, cin, cout, tile_n, L_.stream()))
     torch.cuda.synchronize()
     assert rel_err(nchw(out), want) < TF32_TOL
     # no transform: the plain conv of x
     out2 = torch.full((B, H, W, cout), float("nan"), device=DEV)
-    L_.check(lib().osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), None, 0, None, 0, 0, L_.ptr(out2), cout, B, H, W, cin, cout, 10, 0,
+    L_.check(lib().osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), None, 0, None, 0, 0, L_.ptr(out2), cout, B, H, W, cin, cout, tile_n,
                                      L_.stream()))
     torch.cuda.synchronize()
     assert rel_err(nchw(out2), F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()) < TF32_TOL

@@ -9,11 +9,7 @@ case "$1" in
   refarms)
     python bench.py --impl reference-gpu --steps 20 --warmup 5 > gpurun_out/bench_refgpu.json 2> gpurun_out/bench_refgpu.err; cat gpurun_out/bench_refgpu.json
     python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_refcpu.json 2> gpurun_out/bench_refcpu.err; cat gpurun_out/bench_refcpu.json ;;
-  halo)
-    for v in "10 0" "10 1" "16 0" "16 1"; do for xf in 0 1; do timeout 120 python tools/halo_probe.py $v $xf 2>&1 | tail -3; done; done ;;
   halotime)
-    for shp in "1 256 256 256 256" "4 256 256 256 256" "1 128 128 256 256" "1 128 128 512 512"; do for xf in 0 1; do timeout 300 python tools/halo_probe.py 10 0 $xf $shp --time 2>&1 | tail -2; done; done ;;
-  ncuhalo)
-    ncu --set full --clock-control none --import-source on -k regex:conv_tc_halo -s 2 -c 1 -f -o gpurun_out/halo_xf python tools/halo_probe.py 10 0 1 1 256 256 256 256 --time 2>&1 | tail -4
-    ncu --set full --clock-control none --import-source on -k regex:conv_tc_halo -s 2 -c 1 -f -o gpurun_out/halo_nx python tools/halo_probe.py 10 0 0 1 256 256 256 256 --time 2>&1 | tail -4 ;;
+    for shp in "1 256 256 256 256" "1 256 256 512 256" "4 256 256 256 256" "1 128 128 256 256" "1 128 128 512 512"; do for tn in 256 128; do for xf in 0 1; do timeout 300 python tools/halo_probe.py $tn $xf $shp --time 2>&1 | tail -2 | tr '
+' ' '; echo; done; done; done ;;
 esac

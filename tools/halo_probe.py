@@ -1,5 +1,5 @@
 """Development probe of the halo-tile conv kernel (conv_tc_halo_2sm_kernel): one variant per process.
-usage: python tools/halo_probe.py PITCH BASE_OFFSET XFORM [B H W Cin Cout]"""
+usage: python tools/halo_probe.py TILE_N XFORM [B H W Cin Cout] [--time]"""
 import math
 import os
 import sys
@@ -12,8 +12,8 @@ from osmosis_diffusion_code_b200 import lib as L_  # noqa: E402
 
 
 def main():
-    pitch, bo, xform = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-    B, H, W, cin, cout = [int(v) for v in sys.argv[4:9]] if len(sys.argv) >= 9 else (2, 32, 32, 64, 256)
+    tile_n, xform = int(sys.argv[1]), int(sys.argv[2])
+    B, H, W, cin, cout = [int(v) for v in sys.argv[3:8]] if len(sys.argv) >= 8 else (2, 32, 32, 64, 256)
     lib = L_.load()
     dev = "cuda"
     g = torch.Generator().manual_seed(1)
@@ -33,14 +33,14 @@ def main():
     cd = coef.contiguous().to(dev)
     bd = bias.to(dev)
     L_.check(lib.osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), L_.ptr(cd) if xform else None, 1, None, 0, 0, L_.ptr(out), cout,
-                                   B, H, W, cin, cout, pitch, bo, L_.stream()))
+                                   B, H, W, cin, cout, tile_n, L_.stream()))
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2).cpu()
     err = float((got - want).abs().max() / want.abs().max())
     nan = int(torch.isnan(got).sum())
     # where is it wrong: interior vs border
     d = (got - want).abs().amax(dim=1)[0]
-    print(f"pitch={pitch} bo={bo} xform={xform} shape=({B},{H},{W},{cin},{cout}): rel err {err:.3e} nan={nan} "
+    print(f"tile_n={tile_n} xform={xform} shape=({B},{H},{W},{cin},{cout}): rel err {err:.3e} nan={nan} "
           f"interior {float(d[2:-2, 2:-2].max()):.2e} border {float(d.max()):.2e}  {'OK' if err < 3e-3 and nan == 0 else 'FAIL'}", flush=True)
     if "--time" in sys.argv:
         ts = []
@@ -48,7 +48,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             lib.osm_dbg_conv_halo(L_.ptr(xd), cin, L_.ptr(wf), L_.ptr(bd), L_.ptr(cd) if xform else None, 1, None, 0, 0, L_.ptr(out), cout,
-                                  B, H, W, cin, cout, pitch, bo, L_.stream())
+                                  B, H, W, cin, cout, tile_n, L_.stream())
             e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts[2:])[len(ts[2:]) // 2]
