@@ -241,6 +241,14 @@ int osm_dbg_conv_stats(const float* x, int ldx, const float* w_packed, const flo
  * nn.py:17-19 + unet.py:315-335).  tile_n: 128 / 256 = output channels per CTA-pair tile, 0 = chosen by the plan. */
 int osm_dbg_conv_halo(const float* x, int ldx, const float* w_packed, const float* bias, const float* coef, int silu, const float* res,
                       int ldr, int res_mode, float* out, int ldo, int B, int H, int W, int Cin, int Cout, int tile_n, void* stream);
+/* The fp16-operand variant of the halo kernel (tcgen05 kind::f16, fp32 accumulation): x stays fp32 in memory and is converted
+ * (after the optional x a + b / SiLU transform, coef as above) to fp16 in shared memory; w_packed_f16 is the fp16 pack
+ * [9][Cin/64][Cout][64] written by osm_dbg_pack_conv_weight_f16.  Cin % 64 == 0. */
+int osm_dbg_conv_halo16(const float* x, int ldx, const void* w_packed_f16, const float* bias, const float* coef, int silu,
+                        const float* res, int ldr, int res_mode, float* out, int ldo, int accumulate, int B, int H, int W, int Cin,
+                        int Cout, void* stream);
+int osm_dbg_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p, int taps,
+                                 void* stream);
 int osm_dbg_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p,
                              int taps, int round_tf32, void* stream);
 int osm_dbg_gn_forward(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,

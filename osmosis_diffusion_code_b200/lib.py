@@ -69,6 +69,8 @@ SIGNATURES = {
     "osm_degamma": (_I, [_P, _P, _L, _P]),
     "osm_dbg_conv": (_I, [_I, _P, _I, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "osm_dbg_conv_halo": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "osm_dbg_conv_halo16": (_I, [_P, _I, _P, _P, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "osm_dbg_pack_conv_weight_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "osm_dbg_pack_conv_weight": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "osm_dbg_gn_forward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "osm_dbg_gn_backward": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P]),

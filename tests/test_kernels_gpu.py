@@ -429,3 +429,108 @@ def test_conv_halo_fused_groupnorm_silu(B, H, W, cin, cout, mod, res, tile_n):
                                      L_.stream()))
     torch.cuda.synchronize()
     assert rel_err(nchw(out2), F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()) < TF32_TOL
+
+
+def pack_weight_f16(w):
+    cout, cin = w.shape[:2]
+    wf = torch.zeros(9 * cout * cin, dtype=torch.float16, device=DEV)
+    wd = torch.zeros(9 * cout * cin, dtype=torch.float16, device=DEV)
+    wdev = w.contiguous().to(DEV)
+    L_.check(lib().osm_dbg_pack_conv_weight_f16(L_.ptr(wdev), L_.ptr(wf), L_.ptr(wd), cout, cin, cout, cin, 9, L_.stream()))
+    return wf, wd
+
+
+HALO16_CASES = [
+    # B, H, W, Cin, Cout, modulation, residual
+    (1, 32, 32, 64, 256, False, False),
+    (2, 16, 24, 128, 256, True, True),     # 6 tiles
+    (3, 16, 8, 64, 512, True, False),      # 3 tiles: an odd count leaves the last pair half empty; two N tiles
+    (1, 64, 64, 256, 256, True, True),     # 4 K blocks: the raw / operand rings wrap
+    (2, 32, 32, 256, 512, False, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,mod,res", HALO16_CASES)
+def test_conv_halo16_fp16_operands(B, H, W, cin, cout, mod, res):
+    """The fp16-operand halo kernel (conv_tc_halo16_2sm_kernel: raw fp32 halo boxes by TMA, transform warps write fp16 operand
+    rows, tcgen05 kind::f16 with fp32 accumulation) against torch in float64:
+      * conv2d(SiLU(group_norm(x) (1 + scale) + shift)) (+ residual)   - transform mode 2 (nn.py:17-19, unet.py:315-335)
+      * conv2d(group_norm(x))                                           - mode 1 (no activation)
+      * conv2d(x), with `+=` into the output                            - mode 0 (conversion only)
+      * the input gradient through the flipped / transposed fp16 pack   - mode 0
+    fp16 and TF32 carry the same 11-bit significand, so the tolerance is the TF32 one."""
+    g = torch.Generator().manual_seed(H * W + cin + 1)
+    x = torch.randn(B, cin, H, W, generator=g) * 1.5 + 0.3
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    bias = torch.randn(cout, generator=g)
+    gamma, beta = 1 + 0.2 * torch.randn(cin, generator=g), 0.2 * torch.randn(cin, generator=g)
+    ss = 0.3 * torch.randn(B, 2 * cin + 8, generator=g) if mod else None
+    resid = torch.randn(B, cout, H, W, generator=g) if res else None
+    y = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    y1 = y
+    if mod:
+        y = y * (1 + ss[:, :cin, None, None]) + ss[:, cin:2 * cin, None, None]
+    want = F.conv2d(F.silu(y).double(), w.double(), bias.double(), padding=1).float() + (resid if res else 0.0)
+    xg = x.view(B, 32, -1)
+    mean = xg.mean(-1).repeat_interleave(cin // 32, 1).to(DEV)
+    rstd = (1.0 / torch.sqrt(xg.var(-1, unbiased=False) + 1e-5)).repeat_interleave(cin // 32, 1).to(DEV)
+    sc1 = (1 + ss[:, :cin]).to(DEV) if mod else torch.ones(B, cin, device=DEV)
+    sh = ss[:, cin:2 * cin].to(DEV) if mod else torch.zeros(B, cin, device=DEV)
+    ga, be = gamma.to(DEV), beta.to(DEV)
+    coef = torch.empty(B, cin, 2, device=DEV)
+    coef[..., 0] = rstd * ga * sc1
+    coef[..., 1] = (be - mean * rstd * ga) * sc1 + sh
+    coef1 = torch.empty(B, cin, 2, device=DEV)       # GroupNorm alone
+    coef1[..., 0] = rstd * ga
+    coef1[..., 1] = be - mean * rstd * ga
+    xd = nhwc(x)
+    wf, wd = pack_weight_f16(w)
+    bd = bias.to(DEV)
+    rd_ = nhwc(resid) if res else None
+
+    def run(xin, wp, b_, cf, silu, r_, out, acc, ci, co):
+        L_.check(lib().osm_dbg_conv_halo16(L_.ptr(xin), ci, L_.ptr(wp), L_.ptr(b_), L_.ptr(cf), silu, L_.ptr(r_), co if r_ is not None else 0,
+                                           1 if r_ is not None else 0, L_.ptr(out), co, acc, B, H, W, ci, co, L_.stream()))
+        torch.cuda.synchronize()
+
+    out = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    run(xd, wf, bd, coef, 1, rd_, out, 0, cin, cout)
+    assert torch.isfinite(out).all()
+    assert rel_err(nchw(out), want) < TF32_TOL
+    out1 = torch.full((B, H, W, cout), float("nan"), device=DEV)
+    run(xd, wf, bd, coef1, 0, None, out1, 0, cin, cout)
+    assert rel_err(nchw(out1), F.conv2d(y1.double(), w.double(), bias.double(), padding=1).float()) < TF32_TOL
+    plain = F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    prev = torch.randn(B, cout, H, W, generator=g)
+    out2 = nhwc(prev)
+    run(xd, wf, bd, None, 0, None, out2, 1, cin, cout)
+    assert rel_err(nchw(out2), plain + prev) < TF32_TOL
+    if cin % 256 == 0:   # the dgrad conv has Cin output channels: pair tiles of 256
+        gy = torch.randn(B, cout, H, W, generator=g)
+        xr = x.clone().requires_grad_(True)
+        (gref,) = torch.autograd.grad(F.conv2d(xr.double(), w.double(), bias.double(), padding=1), xr, gy.double())
+        gx = torch.full((B, H, W, cin), float("nan"), device=DEV)
+        run(nhwc(gy), wd, None, None, 0, None, gx, 0, cout, cin)
+        assert rel_err(nchw(gx), gref.float()) < TF32_TOL
+
+
+def test_conv_halo16_small_magnitudes_need_the_power_of_two_prescale():
+    """Gradient-sized operands (1e-6 per entry) sit in fp16's subnormal range: converted as they are they lose most of their
+    significand; multiplied by a power of two first (what the engine's input-VJP does per image, exactly undone afterwards) the
+    result is as accurate as for O(1) operands."""
+    B, H, W, cin, cout = 1, 32, 32, 64, 256
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, H, W, generator=g) * 1e-6
+    w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    want = F.conv2d(x.double(), w.double(), None, padding=1).float()
+    wf, _ = pack_weight_f16(w)
+    errs = []
+    for scale in (1.0, 2.0 ** 22):
+        out = torch.full((B, H, W, cout), float("nan"), device=DEV)
+        xd = nhwc(x * scale)
+        L_.check(lib().osm_dbg_conv_halo16(L_.ptr(xd), cin, L_.ptr(wf), None, None, 0, None, 0, 0, L_.ptr(out), cout, 0, B, H, W, cin, cout,
+                                           L_.stream()))
+        torch.cuda.synchronize()
+        errs.append(rel_err(nchw(out) / scale, want))
+    print("fp16 operands at 1e-6: rel err without / with the power-of-two prescale:", errs)
+    assert errs[1] < TF32_TOL and errs[0] > 3 * errs[1]

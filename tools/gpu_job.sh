@@ -3,13 +3,15 @@
 mkdir -p gpurun_out
 case "$1" in
   tests)
-    python -m pytest tests -m gpu -x -q ${2:+-k "$2"} -s 2>&1 | tail -150 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
+    timeout 1500 python -m pytest tests -m gpu -x -q ${2:+-k "$2"} -s 2>&1 | tail -150 > gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
   bench)
-    python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.err; head -c 3000 gpurun_out/bench_n1.json ;;
+    timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.err; head -c 3000 gpurun_out/bench_n1.json ;;
   refarms)
     python bench.py --impl reference-gpu --steps 20 --warmup 5 > gpurun_out/bench_refgpu.json 2> gpurun_out/bench_refgpu.err; cat gpurun_out/bench_refgpu.json
     python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_refcpu.json 2> gpurun_out/bench_refcpu.err; cat gpurun_out/bench_refcpu.json ;;
-  halotime)
-    for shp in "1 256 256 256 256" "1 256 256 512 256" "4 256 256 256 256" "1 128 128 256 256" "1 128 128 512 512"; do for tn in 256 128; do for xf in 0 1; do timeout 300 python tools/halo_probe.py $tn $xf $shp --time 2>&1 | tail -2 | tr '
-' ' '; echo; done; done; done ;;
+  h16)
+    for mode in 0 1 2; do timeout 120 python tools/halo16_probe.py $mode 2 32 32 64 256 2>&1 | tail -3; done
+    timeout 120 python tools/halo16_probe.py 2 1 64 64 256 256 2>&1 | tail -3
+    timeout 120 python tools/halo16_probe.py 2 3 16 8 128 512 2>&1 | tail -3
+    for shp in "1 256 256 256 256" "1 256 256 512 256" "4 256 256 256 256" "1 128 128 256 256" "1 64 64 512 512" "8 64 64 512 512" "8 32 32 512 512"; do for mode in 0 2; do timeout 300 python tools/halo16_probe.py $mode $shp --time 2>&1 | tail -2 | tr '\n' ' '; echo; done; done ;;
 esac
