@@ -539,3 +539,39 @@ def test_unet_with_groupnorm_fused_into_the_conv_operand_vs_reference_golden(mon
     assert kinds.count("gn_apply") < kinds_base.count("gn_apply")
     print("forward launches with / without the fused operand transform:", m.launch_counts()[0], n_base,
           "gn_apply ops", kinds.count("gn_apply"), "vs", kinds_base.count("gn_apply"))
+
+
+def test_unet_with_fp16_operand_convs_vs_reference_golden(monkeypatch):
+    """OSM_CONV_F16=2 puts every 3x3 conv whose shape allows it (forward and input-gradient, with the GroupNorm + SiLU operand
+    transform, the fused forward / backward statistics epilogues and the power-of-two prescale of the cotangent) on the
+    fp16-operand tcgen05 kernel (conv_tc_halo16_2sm_kernel).  fp16 and TF32 carry the same 11-bit significand, so output and
+    input-VJP must meet the SAME product-mode tolerance against the unmodified reference's golden as the TF32 kernels, and
+    the error must not be larger than theirs by more than rounding noise; a cotangent scaled down to 1e-9 of its size (far
+    below fp16's range) must give exactly 1e-9 of the gradient's accuracy class (the prescale makes the VJP scale-free)."""
+    gold = golden()
+    x, t, cot = case_inputs("unet")
+    monkeypatch.setenv("OSM_CONV_F16", "0")
+    m32 = _model("tc")
+    monkeypatch.setenv("OSM_CONV_F16", "2")
+    m16 = _model("tc")
+    kinds = {}
+    errs = {}
+    for name, m in (("tf32", m32), ("fp16", m16)):
+        xd = x.to(DEV).requires_grad_(True)
+        out = m(xd, t.to(DEV))
+        (gx,) = torch.autograd.grad(out, xd, cot.to(DEV))
+        torch.cuda.synchronize()
+        errs[name] = (rel_err(out.detach().cpu(), gold["unet_out"]), rel_err(gx.cpu(), gold["unet_gx"]))
+        kinds[name] = m.launch_counts()
+    print("UNet error vs the reference golden (output, input-VJP): tf32 convs", errs["tf32"], "fp16-operand convs", errs["fp16"],
+          "launches", kinds)
+    assert errs["fp16"][0] < 1e-2 and errs["fp16"][1] < 1e-2
+    assert errs["fp16"][0] < 2 * errs["tf32"][0] + 1e-4 and errs["fp16"][1] < 2 * errs["tf32"][1] + 1e-4
+    # scale invariance of the input-VJP: tiny and huge cotangents
+    xd = x.to(DEV).requires_grad_(True)
+    out = m16(xd, t.to(DEV))
+    (g1,) = torch.autograd.grad(out, xd, cot.to(DEV), retain_graph=True)
+    for s in (2.0 ** -30, 2.0 ** 20):
+        xs = x.to(DEV).requires_grad_(True)
+        (g2,) = torch.autograd.grad(m16(xs, t.to(DEV)), xs, (cot * s).to(DEV))
+        assert torch.equal(g2 / s, g1), f"the input-VJP is not exactly linear under a power-of-two scale of {s}"

@@ -14,4 +14,9 @@ case "$1" in
     timeout 120 python tools/halo16_probe.py 2 1 64 64 256 256 2>&1 | tail -3
     timeout 120 python tools/halo16_probe.py 2 3 16 8 128 512 2>&1 | tail -3
     for shp in "1 256 256 256 256" "1 256 256 512 256" "4 256 256 256 256" "1 128 128 256 256" "1 64 64 512 512" "8 64 64 512 512" "8 32 32 512 512"; do for mode in 0 2; do timeout 300 python tools/halo16_probe.py $mode $shp --time 2>&1 | tail -2 | tr '\n' ' '; echo; done; done ;;
+  prof)
+    timeout 600 python tools/profile_step.py --batch 1 > gpurun_out/step_breakdown_b1.log 2>&1
+    timeout 900 python tools/profile_step.py --batch ${2:-32} > gpurun_out/step_breakdown_b${2:-32}.log 2>&1 ;;
+  ncu16)
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:halo16 -s 2 -c 1 -f -o gpurun_out/ncu_halo16 python tools/halo16_probe.py ${2:-2} ${3:-4 256 256 256 256} --time > gpurun_out/ncu16.log 2>&1; tail -3 gpurun_out/ncu16.log ;;
 esac
