@@ -236,6 +236,11 @@ int osm_dbg_conv_stats(const float* x, int ldx, const float* w_packed, const flo
                        int W, int Cin, int Cout, int taps, int mode, const float* gn_x, int gn_ldx, const float* gamma,
                        const float* beta, const float* scale_shift, int ld_ss, int silu, const float* fwd_stats,
                        float* scratch_partial, float* scratch_coef, float* stats_out, int* fused, void* stream);
+/* the same through the fp16-operand halo kernel (w_packed_f16 from osm_dbg_pack_conv_weight_f16; 3x3, Cin % 64 == 0, Cout % 256 == 0) */
+int osm_dbg_conv_stats_f16(const float* x, int ldx, const void* w_packed_f16, const float* bias, float* out, int ldo, int B, int H,
+                           int W, int Cin, int Cout, int taps, int mode, const float* gn_x, int gn_ldx, const float* gamma,
+                           const float* beta, const float* scale_shift, int ld_ss, int silu, const float* fwd_stats,
+                           float* scratch_partial, float* scratch_coef, float* stats_out, int* fused, void* stream);
 /* Halo-tile CTA-pair tcgen05 conv (3x3, Cout % 256 == 0, H % 16 == 0, W % 8 == 0).  coef != NULL: [B][Cin] float2 (a, b) and the
  * conv runs on tf32(SiLU?(x a + b)) computed in shared memory from the raw x (GroupNorm + SiLU fused into the operand load,
  * nn.py:17-19 + unet.py:315-335).  tile_n: 128 / 256 = output channels per CTA-pair tile, 0 = chosen by the plan. */
@@ -247,6 +252,10 @@ int osm_dbg_conv_halo(const float* x, int ldx, const float* w_packed, const floa
 int osm_dbg_conv_halo16(const float* x, int ldx, const void* w_packed_f16, const float* bias, const float* coef, int silu,
                         const float* res, int ldr, int res_mode, float* out, int ldo, int accumulate, int B, int H, int W, int Cin,
                         int Cout, void* stream);
+/* The tile-per-CTA / persistent / CTA-pair tcgen05 kernels on fp16 operands read straight from memory (kind::f16): x_f16 is an NHWC
+ * fp16 tensor (ldx in elements), w_packed_f16 the fp16 pack [taps][Cin/64][Cout][64]; 3x3 or 1x1, Cin % 64 == 0, Cout % 32 == 0. */
+int osm_dbg_conv_f16(const void* x_f16, int ldx, const void* w_packed_f16, const float* bias, const float* res, int ldr, int res_mode,
+                     float* out, int ldo, int accumulate, int B, int H, int W, int Cin, int Cout, int taps, void* stream);
 int osm_dbg_pack_conv_weight_f16(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p, int taps,
                                  void* stream);
 int osm_dbg_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int Cout_p, int Cin_p,
@@ -257,6 +266,13 @@ int osm_dbg_gn_backward(const float* x, int ldx, const float* gamma, const float
                         int ld_ss, int silu, int resample, const float* stats, const float* dy, const float* addend,
                         int ld_add, int add_mode, float* dx, int ld_dx, int accumulate, int B, int H, int W, int C,
                         void* stream);
+/* the same two with the output written as fp16 elements (the operand of an fp16 tensor-core conv; backward: accumulate must be 0) */
+int osm_dbg_gn_forward_f16(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,
+                           int ld_ss, int silu, int resample, float* stats, void* y_f16, int B, int H, int W, int C, void* stream);
+int osm_dbg_gn_backward_f16(const float* x, int ldx, const float* gamma, const float* beta, const float* scale_shift,
+                            int ld_ss, int silu, int resample, const float* stats, const float* dy, const float* addend,
+                            int ld_add, int add_mode, void* dx_f16, int ld_dx, int accumulate, int B, int H, int W, int C,
+                            void* stream);
 int osm_dbg_attention(const float* qkv, float* out, float* scratch_P, int B, int L, int C, int heads, void* stream);
 int osm_dbg_attention_bwd(const float* qkv, const float* g_out, float* g_qkv, float* scratch_P, float* scratch_D, int B,
                           int L, int C, int heads, void* stream);

@@ -279,8 +279,9 @@ def test_flash_attention_forward_backward(B, L, Cc, heads):
     assert torch.equal(out, out2) and torch.equal(gq, gq2)
 
 
-@pytest.mark.parametrize("cout,silu,mod", [(256, 1, True), (512, 0, False), (128, 1, False)])
-def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
+@pytest.mark.parametrize("cout,silu,mod,f16", [(256, 1, True, False), (512, 0, False, False), (128, 1, False, False),
+                                               (256, 1, True, True), (512, 0, False, True), (512, 1, True, True)])
+def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod, f16):
     """GroupNorm statistics reduced in the tcgen05 conv's epilogue (conv_epilogue.cuh) + the finalize kernel, checked
     against torch statistics of the conv's OWN output (so the TF32 rounding of the conv itself does not enter):
     mode 1 = forward mean / rstd (nn.py:17-19); mode 2 = the two means of the GroupNorm input gradient."""
@@ -290,14 +291,17 @@ def test_conv_epilogue_fused_groupnorm_statistics(cout, silu, mod):
     w = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * taps)
     bias = (torch.randn(cout, generator=g) + 0.5).to(DEV)
     wf, _, cout_p, cin_p = pack_weight(w, taps, round_tf32=True)
+    if f16:   # the fp16-operand halo kernel (8 x 16-pixel tiles: the same 4 partial slots per 128-pixel tile)
+        wf, _ = pack_weight_f16(w)
     out = torch.empty(B, H, W, cout, device=DEV)
     part = torch.full((B * 256 * 4 * 64,), float("nan"), device=DEV)
     coef = torch.empty(B * cout * 4, device=DEV)
     stats = torch.zeros(B, 32, 2, device=DEV)
     fused = C.c_int(0)
+    entry = lib().osm_dbg_conv_stats_f16 if f16 else lib().osm_dbg_conv_stats
 
     def call(mode, gx=None, gamma=None, beta=None, ss=None, fstats=None, dst=None):
-        L_.check(lib().osm_dbg_conv_stats(L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(out), cout, B, H, W, cin, cout, taps, mode,
+        L_.check(entry(L_.ptr(x), cin, L_.ptr(wf), L_.ptr(bias), L_.ptr(out), cout, B, H, W, cin, cout, taps, mode,
                                           L_.ptr(gx), cout, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * cout, silu, L_.ptr(fstats),
                                           L_.ptr(part), L_.ptr(coef), L_.ptr(dst), C.addressof(fused), L_.stream()))
         torch.cuda.synchronize()
@@ -534,3 +538,94 @@ def test_conv_halo16_small_magnitudes_need_the_power_of_two_prescale():
         errs.append(rel_err(nchw(out) / scale, want))
     print("fp16 operands at 1e-6: rel err without / with the power-of-two prescale:", errs)
     assert errs[1] < TF32_TOL and errs[0] > 3 * errs[1]
+
+
+NH16_CASES = [
+    # B, H, W, Cin, Cout, taps : the shapes the halo kernels do not take (small images, 1x1 convs, narrow outputs)
+    (1, 8, 8, 1024, 1024, 9),      # cluster split-K
+    (1, 16, 16, 512, 1024, 9),
+    (2, 32, 32, 256, 256, 9),
+    (1, 32, 32, 512, 1536, 1),
+    (3, 8, 8, 128, 512, 9),
+    (2, 16, 16, 64, 32, 1),
+    (1, 64, 64, 256, 32, 9),       # the 8 (-> 32) channel output conv
+    (8, 32, 32, 512, 1536, 1),     # persistent / CTA-pair plans
+    (4, 64, 64, 64, 256, 1),
+]
+
+
+@pytest.mark.parametrize("case", NH16_CASES, ids=[str(c) for c in NH16_CASES])
+def test_conv_fp16_operands_from_memory(case):
+    """The tile-per-CTA (cluster split-K), persistent and CTA-pair tcgen05 kernels in kind::f16: the activation tensor is fp16 in
+    memory (written that way by the GroupNorm kernels, checked separately), weights from the fp16 pack; forward, residual / `+=`
+    epilogues and the input gradient against torch in float64 on the fp16-rounded input.  Same tolerance as TF32."""
+    B, H, W, cin, cout, taps = case
+    g = torch.Generator().manual_seed(sum(case) + 11)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * taps)
+    b = torch.randn(cout, generator=g)
+    cout_p = (cout + 31) // 32 * 32
+    wf = torch.zeros(taps * cout_p * cin, dtype=torch.float16, device=DEV)
+    wd = torch.zeros(taps * cout_p * cin, dtype=torch.float16, device=DEV) if cout_p % 64 == 0 else None
+    L_.check(lib().osm_dbg_pack_conv_weight_f16(L_.ptr(w.contiguous().to(DEV)), L_.ptr(wf), L_.ptr(wd), cout, cin, cout_p, cin, taps, L_.stream()))
+    xh = nhwc(x).half()
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).float()
+    bp = torch.zeros(cout_p, device=DEV); bp[:cout] = b.to(DEV)
+    res = torch.randn(B, cout, H, W, generator=g)
+    rp = torch.zeros(B, H, W, cout_p, device=DEV); rp[..., :cout] = nhwc(res)
+    out = torch.full((B, H, W, cout_p), float("nan"), device=DEV)
+    L_.check(lib().osm_dbg_conv_f16(L_.ptr(xh), cin, L_.ptr(wf), L_.ptr(bp), L_.ptr(rp), cout_p, 1, L_.ptr(out), cout_p, 0, B, H, W, cin, cout_p,
+                                    taps, L_.stream()))
+    torch.cuda.synchronize()
+    got = nchw(out)
+    assert torch.isfinite(got).all()
+    assert rel_err(got[:, :cout], ref + res) < TF32_TOL
+    prev = out.clone()
+    L_.check(lib().osm_dbg_conv_f16(L_.ptr(xh), cin, L_.ptr(wf), L_.ptr(bp), None, 0, 0, L_.ptr(out), cout_p, 1, B, H, W, cin, cout_p, taps,
+                                    L_.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out)[:, :cout], ref + nchw(prev)[:, :cout]) < TF32_TOL
+    if wd is not None:
+        gy = torch.randn(B, cout, H, W, generator=g)
+        xr = x.clone().requires_grad_(True)
+        (gref,) = torch.autograd.grad(F.conv2d(xr.double(), w.double(), b.double(), padding=k // 2), xr, gy.double())
+        gyp = torch.zeros(B, H, W, cout_p, device=DEV); gyp[..., :cout] = nhwc(gy)
+        gx = torch.full((B, H, W, cin), float("nan"), device=DEV)
+        L_.check(lib().osm_dbg_conv_f16(L_.ptr(gyp.half()), cout_p, L_.ptr(wd), None, None, 0, 0, L_.ptr(gx), cin, 0, B, H, W, cout_p, cin, taps,
+                                        L_.stream()))
+        torch.cuda.synchronize()
+        assert rel_err(nchw(gx), gref.float()) < TF32_TOL
+
+
+@pytest.mark.parametrize("H,Cc", [(16, 256), (32, 512)], ids=["one-launch", "two-kernel"])
+def test_groupnorm_kernels_write_fp16_operands(H, Cc):
+    """GroupNorm apply (both the two-kernel and the one-launch path, with and without resampling) and GroupNorm backward writing
+    their output as fp16 (the operand of an fp16 conv): equal to the fp32 output rounded to fp16 (RN)."""
+    B, W = 2, H
+    g = torch.Generator().manual_seed(21)
+    x = nhwc(torch.randn(B, Cc, H, W, generator=g) * 1.3 + 0.2)
+    gamma = (1 + 0.2 * torch.randn(Cc, generator=g)).to(DEV); beta = (0.2 * torch.randn(Cc, generator=g)).to(DEV)
+    ss = (0.3 * torch.randn(B, 2 * Cc, generator=g)).to(DEV)
+    stats = torch.zeros(B, 32, 2, device=DEV)
+    for rs, (Ho, Wo) in ((0, (H, W)), (1, (H // 2, W // 2)), (2, (2 * H, 2 * W))):
+        y32 = torch.empty(B, Ho, Wo, Cc, device=DEV)
+        L_.check(lib().osm_dbg_gn_forward(L_.ptr(x), Cc, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * Cc, 1, rs, L_.ptr(stats), L_.ptr(y32), B, H, W, Cc,
+                                          L_.stream()))
+        y16 = torch.zeros(B, Ho, Wo, Cc, dtype=torch.float16, device=DEV)
+        L_.check(lib().osm_dbg_gn_forward_f16(L_.ptr(x), Cc, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * Cc, 1, rs, L_.ptr(stats), L_.ptr(y16), B, H, W,
+                                              Cc, L_.stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(y16, y32.half()), f"resample {rs}"
+    dy = nhwc(torch.randn(B, Cc, H, W, generator=g))
+    y32 = torch.empty(B, H, W, Cc, device=DEV)
+    L_.check(lib().osm_dbg_gn_forward(L_.ptr(x), Cc, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * Cc, 1, 0, L_.ptr(stats), L_.ptr(y32), B, H, W, Cc,
+                                      L_.stream()))
+    dx32 = torch.empty(B, H, W, Cc, device=DEV)
+    dx16 = torch.zeros(B, H, W, Cc, dtype=torch.float16, device=DEV)
+    L_.check(lib().osm_dbg_gn_backward(L_.ptr(x), Cc, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * Cc, 1, 0, L_.ptr(stats), L_.ptr(dy), None, 0, 0,
+                                       L_.ptr(dx32), Cc, 0, B, H, W, Cc, L_.stream()))
+    L_.check(lib().osm_dbg_gn_backward_f16(L_.ptr(x), Cc, L_.ptr(gamma), L_.ptr(beta), L_.ptr(ss), 2 * Cc, 1, 0, L_.ptr(stats), L_.ptr(dy), None, 0, 0,
+                                           L_.ptr(dx16), Cc, 0, B, H, W, Cc, L_.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(dx16, dx32.half())
