@@ -397,7 +397,10 @@ def run_native(args):
         if world > 1: dist.destroy_process_group()
         return
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_step, higher_is_better=True,
-               scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
+               scaling="weak", vs_baseline=None, dtype="f16|tf32 operands, f32 accumulate", data="synthetic",
+               dtype_note="tensor-core operands carry an 11-bit significand everywhere (fp16 where a kernel of ours produces or converts the "
+                          "operand, TF32 elsewhere: what cuDNN runs for the reference on a GPU); accumulation, GroupNorm, softmax, sampler "
+                          "and guidance are fp32; OSM_CONV_F16=0 selects TF32 for every conv",
                config=dict(workload=workload_name(args.config, B, args.size, 1000, K, T), batch_per_gpu=B,
                            global_batch=B * world, image=args.size, unet_params=model.num_params(), parallelism=f"dp{world} (batch-sharded, no collective)",
                            l2="per-step working set (2.2 GB weights + 1.6 GB activations per image) exceeds the 126 MB L2"),
@@ -429,21 +432,36 @@ def dominant_roofline(args, model, dev):
     dom = [o for o in conv if o["dims"][:5] == [args.size, args.size, 256, 256, 9]] or conv
     dom_ms = sum(o["ms"] for o in dom) / len(dom)
     dom_tf = dom[0]["flops"] / dom_ms / 1e9
+    opk = sorted({o["dims"][5] >> 1 for o in dom})      # operand type of those launches: 0 TF32, 1 fp16 halo kernel, 2 fp16 from memory
+    f16 = opk == [1]
+    by_operand = {}
+    for o in conv:
+        d = by_operand.setdefault(("tf32", "fp16 halo kernel", "fp16 from memory")[o["dims"][5] >> 1], [0.0, 0.0, 0])
+        d[0] += o["flops"]; d[1] += o["ms"]; d[2] += 1
     conv_all_tf = sum(o["flops"] for o in conv) / sum(o["ms"] for o in conv) / 1e9
     norm = [o for o in prof if o["kind"].startswith("gn")]
     norm_gbs = sum(o["bytes"] for o in norm) / sum(o["ms"] for o in norm) / 1e6
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_conv_traffic.json")
+    tsrc = None
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        ent = tj.get("fp16_halo" if f16 else "tf32_pair", tj)
+        traffic, tsrc = ent.get("dram_bytes_per_launch"), ent.get("source")
     tf32 = measure_tf32_peak(dev)
-    roofline = dict(bound="tensor", kernel="conv_tc_persist_2sm_kernel<6,.> (3x3 256->256 @256x256 tcgen05 cta_group::2 TF32 implicit GEMM, fwd + dgrad launches)",
+    kname = ("conv_tc_halo16_2sm_kernel (3x3 256->256 @256x256: tcgen05 cta_group::2 kind::f16 implicit GEMM on halo tiles, fp32 input "
+             "converted / GroupNorm+SiLU-transformed to fp16 in shared memory, fp32 accumulation in TMEM; fwd + dgrad launches)") if f16 else \
+            "conv_tc_persist_2sm_kernel<6,.> (3x3 256->256 @256x256 tcgen05 cta_group::2 TF32 implicit GEMM, fwd + dgrad launches)"
+    roofline = dict(bound="tensor", kernel=kname,
                     achieved=round(dom_tf, 1), peak=peaks["bf16_sustained"], unit="TFLOP/s",
                     frac=round(dom_tf / peaks["bf16_sustained"], 4), traffic=traffic,
-                    traffic_source="ncu --set full capture of this kernel (profiles/ncu_conv_traffic.json), per launch",
+                    traffic_source=tsrc or "ncu --set full capture of this kernel (profiles/ncu_conv_traffic.json), per launch",
                     peak_source=f"{peaks['source']} bf16 sustained from MEASURED_PEAKS.json (kernel timed inside the step)",
-                    dtype_note="the kernel computes in TF32 (the reference's own GPU arithmetic for conv); cuBLAS TF32 8192^3 measured "
-                               "in this run the same way is the like-for-like denominator",
+                    dtype_note=("fp16 operands (11-bit significand, the same as TF32 = the reference's own GPU arithmetic for conv), fp32 accumulation; "
+                                "the dense 16-bit peak is the denominator" if f16 else
+                                "the kernel computes in TF32 (the reference's own GPU arithmetic for conv); cuBLAS TF32 8192^3 measured "
+                                "in this run the same way is the like-for-like denominator"),
+                    convs_by_operand={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms=round(v[1], 3), launches=v[2]) for k, v in by_operand.items()},
                     tf32_peak_measured=tf32, frac_of_tf32_sustained=round(dom_tf / tf32["tf32_tflops_sustained"], 4),
                     flops_per_launch=dom[0]["flops"], launches_averaged=len(dom), ms_per_launch=round(dom_ms, 4),
                     all_convs_tflops=round(conv_all_tf, 1), groupnorm_kernels_gbs=round(norm_gbs, 0), hbm_peak_gbs=peaks["hbm"],

@@ -19,4 +19,9 @@ case "$1" in
     timeout 900 python tools/profile_step.py --batch ${2:-32} > gpurun_out/step_breakdown_b${2:-32}.log 2>&1 ;;
   ncu16)
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:halo16 -s 2 -c 1 -f -o gpurun_out/ncu_halo16 python tools/halo16_probe.py ${2:-2} ${3:-4 256 256 256 256} --time > gpurun_out/ncu16.log 2>&1; tail -3 gpurun_out/ncu16.log ;;
+  launches)
+    # ncu launch list of ONE steady-state region of the bench (cold-cache, serialised per-launch times: compare shares)
+    timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 2 --warmup 3 --no-table --no-cpu-baseline --no-eager-reference --profiler-range > gpurun_out/launches_bench.log 2>&1
+    tail -2 gpurun_out/launches_bench.log | cut -c1-300; wc -l gpurun_out/launches.csv ;;
 esac
