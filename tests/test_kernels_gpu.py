@@ -451,6 +451,9 @@ HALO16_CASES = [
     (3, 16, 8, 64, 512, True, False),      # 3 tiles: an odd count leaves the last pair half empty; two N tiles
     (1, 64, 64, 256, 256, True, True),     # 4 K blocks: the raw / operand rings wrap
     (2, 32, 32, 256, 512, False, True),
+    # ONE 64-channel pair tile: the 8-channel output conv / the 4-channel input conv's gradient (channels padded to 64)
+    (1, 32, 32, 256, 64, True, False),
+    (3, 16, 16, 64, 64, False, True),
 ]
 
 
