@@ -24,4 +24,7 @@ case "$1" in
     timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 2 --warmup 3 --no-table --no-cpu-baseline --no-eager-reference --profiler-range > gpurun_out/launches_bench.log 2>&1
     tail -2 gpurun_out/launches_bench.log | cut -c1-300; wc -l gpurun_out/launches.csv ;;
+  ncu16s)
+    for m in 1 2; do timeout 120 python tools/halo16_stats_probe.py $m 4 256 256 256 256 2>&1 | tail -1; done
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:halo16 -s 2 -c 1 -f -o gpurun_out/ncu_halo16s python tools/halo16_stats_probe.py 2 4 256 256 256 256 > gpurun_out/ncu16s.log 2>&1; tail -2 gpurun_out/ncu16s.log ;;
 esac
