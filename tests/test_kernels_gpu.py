@@ -146,6 +146,11 @@ GN_CASES = [
     (3, 8, 8, 1536, 0, 0, 0),
     (1, 4, 4, 2048, 1, 1, 0),
     (2, 64, 64, 128, 1, 0, 0),
+    # one-launch kernel on a thread-block cluster per (image, group) (batch < 4, more than 4096 elements per group):
+    (2, 16, 16, 1024, 1, 0, 0),    # 2 CTAs
+    (1, 32, 32, 512, 1, 1, 0),     # 4 CTAs
+    (1, 24, 24, 768, 1, 1, 0),     # 4 CTAs, 6 four-channel slots per group (idle tail threads)
+    (1, 32, 32, 1024, 0, 0, 0),    # 8 CTAs
 ]
 
 
@@ -599,6 +604,66 @@ def test_conv_fp16_operands_from_memory(case):
                                         L_.stream()))
         torch.cuda.synchronize()
         assert rel_err(nchw(gx), gref.float()) < TF32_TOL
+
+
+SPLITK_CASES = [
+    # B, H, W, Cin, Cout, taps, forced BN, forced split, residual mode
+    (1, 8, 8, 512, 256, 9, 64, 16, 1),     # half of the 128 tile rows are padding; one float4 column per rank
+    (1, 8, 8, 512, 256, 9, 256, 8, 0),
+    (1, 16, 16, 256, 512, 9, 128, 4, 2),   # residual from the 2x finer level (avg-pool)
+    (2, 16, 16, 512, 128, 1, 128, 2, 3),   # residual from the 2x coarser level (nearest-up)
+    (3, 8, 8, 256, 256, 1, 64, 4, 1),      # three images in tiles of two: the last tile is half empty
+    (1, 32, 32, 256, 512, 9, 256, 2, 0),
+    (1, 8, 8, 256, 256, 1, 32, 2, 1),
+]
+
+
+@pytest.mark.parametrize("f16", [False, True], ids=["tf32", "fp16"])
+@pytest.mark.parametrize("case", SPLITK_CASES, ids=[str(c) for c in SPLITK_CASES])
+def test_conv_cluster_split_k_l2_and_dsmem_reductions(case, f16, monkeypatch):
+    """conv_tc_kernel's split-K reduction through the L2 scratch (the default) against torch, and bit for bit against the reduction
+    through distributed shared memory (OSM_CONV_SKRED=0: same partials, same rank order), for forced (BN, split) variants, every
+    residual mode and `+=`."""
+    B, H, W, cin, cout, taps, bn, split, res_mode = case
+    g = torch.Generator().manual_seed(sum(case) + 3)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * taps)
+    b = torch.randn(cout, generator=g)
+    res = {0: None, 1: torch.randn(B, cout, H, W, generator=g), 2: torch.randn(B, cout, 2 * H, 2 * W, generator=g),
+           3: torch.randn(B, cout, H // 2, W // 2, generator=g)}[res_mode]
+    prev = torch.randn(B, cout, H, W, generator=g)
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).float() + prev
+    if res_mode == 1:
+        want = want + res
+    elif res_mode == 2:
+        want = want + F.avg_pool2d(res, 2, 2)
+    elif res_mode == 3:
+        want = want + F.interpolate(res, scale_factor=2, mode="nearest")
+    rdev = nhwc(res) if res is not None else None
+    bdev = b.to(DEV)
+    if f16:
+        wp = torch.zeros(taps * cout * cin, dtype=torch.float16, device=DEV)
+        L_.check(lib().osm_dbg_pack_conv_weight_f16(L_.ptr(w.contiguous().to(DEV)), L_.ptr(wp), None, cout, cin, cout, cin, taps, L_.stream()))
+        xdev = nhwc(x).half()
+    else:
+        wp, _, _, _ = pack_weight(w, taps, round_tf32=True)
+        xdev = nhwc(x)
+    monkeypatch.setenv("OSM_CONV_FORCE", f"{bn},{split}")
+    outs = []
+    for skred in ("1", "0"):
+        monkeypatch.setenv("OSM_CONV_SKRED", skred)
+        out = nhwc(prev)
+        if f16:
+            L_.check(lib().osm_dbg_conv_f16(L_.ptr(xdev), cin, L_.ptr(wp), L_.ptr(bdev), L_.ptr(rdev), cout, res_mode, L_.ptr(out), cout, 1, B, H, W,
+                                            cin, cout, taps, L_.stream()))
+        else:
+            L_.check(lib().osm_dbg_conv(0, L_.ptr(xdev), cin, L_.ptr(wp), L_.ptr(bdev), L_.ptr(rdev), cout, res_mode, L_.ptr(out), cout, 1, B, H, W,
+                                        cin, cout, taps, L_.stream()))
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert rel_err(nchw(outs[0]), want) < TF32_TOL
+    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("H,Cc", [(16, 256), (32, 512)], ids=["one-launch", "two-kernel"])
