@@ -160,6 +160,11 @@ if __name__ == "__main__":
     lib.osm_dbg_trace_read.argtypes = [C.c_void_p, C.c_int]
     lib.osm_dbg_trace_clear.restype = C.c_int
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for a in sys.argv[1:]:
+        if a.startswith("--flags="):   # experiments: 1 = no A loads, 2 = no weight loads, 3 = neither (results are garbage, timing only)
+            lib.osm_dbg_trace_flags.argtypes = [C.c_int]
+            lib.osm_dbg_trace_flags(int(a.split("=")[1]))
+            print("trace flags", a.split("=")[1])
     if "--sweep" in sys.argv:
         for sh in [tuple(int(v) for v in a.split(",")) for a in args] or SWEEP:
             sweep(lib, L_, torch, *sh)
