@@ -189,6 +189,8 @@ int attention_fwd_launch(const float* qkv, float* out, float* P /*[B*heads,L,L]*
 int attention_bwd_launch(const float* qkv, const float* g_out, float* g_qkv, float* P, float* D, int B, int L, int C, int heads,
                          cudaStream_t s);
 int attention_launches(int which);
+// L = 64 tokens with 64 channels per head (the 8x8 level): attention_fwd/bwd_launch are ONE fused fp32 launch each (P / D unused)
+bool attention_small_ok(int L, int C, int heads);
 
 // Fused tcgen05 flash attention (attention_flash.cu).  The plan owns the TMA descriptors of one attention block's buffers.
 struct AttnFlashPlan {

@@ -219,8 +219,9 @@ def test_groupnorm_forward_backward(case, small, monkeypatch):
             assert float(dxbuf[..., Cc:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("B,L,Cc,heads", [(2, 64, 256, 4), (1, 256, 512, 8), (2, 1024, 128, 2), (3, 16, 1024, 16)])
+@pytest.mark.parametrize("B,L,Cc,heads", [(2, 64, 256, 4), (1, 256, 512, 8), (2, 1024, 128, 2), (3, 16, 1024, 16), (3, 64, 1024, 16)])
 def test_attention_forward_backward(B, L, Cc, heads):
+    # (L = 64 with 64 channels per head - the 8x8 level of the shipped UNet - takes the one-launch fused fp32 kernels attn_small_*)
     g = torch.Generator().manual_seed(L + Cc)
     qkv = torch.randn(B, 3 * Cc, L, generator=g).requires_grad_(True)
     ref = orc.qkv_attention_legacy(qkv, heads)  # [B, C, L]
