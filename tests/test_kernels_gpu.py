@@ -61,7 +61,7 @@ CONV_CASES = [
     (2, 4, 4, 256, 256, 9),
     (1, 32, 16, 32, 8, 9),
     (2, 64, 64, 4, 256, 9),
-    # small-M layers: cluster split-K (2/4/8 CTAs per tile, DSMEM reduction)
+    # small-M layers: cluster split-K (2/4/8/16 CTAs per tile, partials reduced through the L2 scratch)
     (1, 8, 8, 1024, 1024, 9),
     (1, 16, 16, 512, 1024, 9),
     (2, 32, 32, 256, 256, 9),
