@@ -151,6 +151,9 @@ GN_CASES = [
     (1, 32, 32, 512, 1, 1, 0),     # 4 CTAs
     (1, 24, 24, 768, 1, 1, 0),     # 4 CTAs, 6 four-channel slots per group (idle tail threads)
     (1, 32, 32, 1024, 0, 0, 0),    # 8 CTAs
+    # from batch 4 one CTA per (image, group) takes up to 32768 elements: more than 4 pixels per thread = the two-pass (not
+    # register-cached) form of the one-launch kernels
+    (4, 32, 32, 256, 1, 1, 0),
 ]
 
 
